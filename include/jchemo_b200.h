@@ -1,0 +1,175 @@
+/*
+ * jchemo_b200.h — C ABI of libjchemo_b200.so (sm_100a), the B200-native replacement for the
+ * kernel-PLS path of Jchemo.jl.
+ *
+ * The reference has no FFI of its own: the boundary it exposes is the exported Julia function API
+ *   plskern / plskern!            /root/reference/src/plskern.jl:106-178   (export: src/Jchemo.jl:247)
+ *   transform / coef / predict    /root/reference/src/plskern.jl:187-238   (export: src/Jchemo.jl:302)
+ * Each entry point below names the reference lines it replaces.  A Julia (or ctypes) host binds
+ * these with `ccall`; see INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *  - every matrix is IEEE Float64, column-major, with an explicit leading dimension (elements);
+ *  - every array is caller-allocated and caller-owned; the library keeps no host pointer after return;
+ *  - return value: 0 = success, < 0 = bad argument, > 0 = CUDA failure (value is the cudaError_t);
+ *    the message is available, per calling thread, from jcb200_last_error();
+ *  - there is NO CPU fallback: without a usable sm_100 device every compute call fails;
+ *  - entry points are re-entrant: one process-wide mutex serialises device work (the GPU is one
+ *    resource; the reference's callers invoke `fun` from Threads.@threads loops, src/locwlv.jl:18);
+ *  - "_dev" entry points take DEVICE pointers (benchmarking without PCIe; multi-process sharding),
+ *    the others take HOST pointers and include the host<->device copies.
+ */
+#ifndef JCHEMO_B200_H
+#define JCHEMO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JCB200_VERSION 100 /* 0.1.0 */
+
+/* status codes (< 0: argument errors) */
+#define JCB200_OK 0
+#define JCB200_EINVAL (-1)   /* n, p, q <= 0; nlv < 0; ld < rows; NULL where an array is required   */
+#define JCB200_ENODEV (-2)   /* no CUDA device, or compute capability != 10.x                      */
+#define JCB200_ENOMEM (-3)   /* device allocation failed                                           */
+#define JCB200_EALIGN (-4)   /* "_dev" pointer not 16-byte aligned or odd leading dimension         */
+
+/* number of phases reported by jcb200_last_timings (ms each, CUDA events on the library stream) */
+#define JCB200_NPHASE 10
+enum jcb200_phase {
+    JCB200_T_H2D = 0,      /* host -> device copies of X, Y, w                       */
+    JCB200_T_PIVOT = 1,    /* strided-sample pivot                                    */
+    JCB200_T_GRAM = 2,     /* K1: fused weight/centre + DMMA SYRK (dominant kernel)   */
+    JCB200_T_REDUCE = 3,   /* K1b: ordered split-K reduce into the packed buffer      */
+    JCB200_T_FINALIZE = 4, /* K3: means, scales, pivot correction, mirror             */
+    JCB200_T_LVLOOP = 5,   /* K4: persistent latent-variable loop                     */
+    JCB200_T_SCORES = 6,   /* K5/K6: (X - mu) * M streaming GEMM (scores / predictions) */
+    JCB200_T_WRITEBACK = 7,/* K7: in-place centring/scaling of X, Y (plskern! only)   */
+    JCB200_T_D2H = 8,      /* device -> host copies                                   */
+    JCB200_T_TOTAL = 9     /* first event to last event of the call                   */
+};
+
+/* ---- library management ------------------------------------------------------------------- */
+int jcb200_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* jcb200_last_error(void);
+/* Bind the library to CUDA device `device` (default 0 on first use). Idempotent. */
+int jcb200_init(int device);
+void jcb200_shutdown(void);
+/* Launch on an external stream (a cudaStream_t, e.g. torch's current stream); NULL = own stream. */
+int jcb200_set_stream(void* cuda_stream);
+/* Per-phase times (ms) of the last successful call; returns the number of phases written. */
+int jcb200_last_timings(double* ms, int cap);
+/* Synchronise the library stream and collect the phase times of the preceding "_dev" calls. */
+int jcb200_sync_timings(void);
+/* Number of kernels this library has launched since load (claim for bench.py's gpu_launches). */
+int64_t jcb200_launch_count(void);
+/* Page-lock / unlock a caller's host array so that the copies run at full PCIe speed. */
+int jcb200_host_register(void* ptr, int64_t bytes);
+int jcb200_host_unregister(void* ptr);
+
+/* ---- host-pointer entry points (the drop-in path) ------------------------------------------- */
+
+/* plskern!/plskern — /root/reference/src/plskern.jl:106-178 with utility.jl:76-81,193-195,262-264,
+ * 312-323,482-487,715-723 folded in.  nlv is clamped to min(n, p, nlv) (:116); *nlv_out receives it.
+ * w == NULL means ones(n) (:106,:112).  writeback_xy != 0 reproduces plskern!'s side effect: X and Y
+ * leave centred (and scaled) in the caller's arrays (:125-129); 0 leaves them untouched (plskern).
+ * Outputs (all required, column-major): T n*nlv (ld = ldt), P,R,W p*nlv (ld = p), C q*nlv (ld = q),
+ * TT nlv, xmeans p, xscales p, ymeans q, yscales q, w_out n (the normalised weights, :117). */
+int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const double* w,
+                       int64_t n, int64_t p, int64_t q, int32_t nlv, int32_t scal,
+                       int32_t writeback_xy,
+                       double* T, int64_t ldt, double* P, double* R, double* W, double* C,
+                       double* TT, double* xmeans, double* xscales, double* ymeans,
+                       double* yscales, double* w_out, int32_t* nlv_out);
+
+/* transform(::Plsr, X; nlv) — plskern.jl:187-195: T_out (m*nlv, ld = ldt) =
+ * ((X - xmeans) ./ xscales) * R[:, 1:nlv].  R has leading dimension p.  nlv == 0 is a no-op. */
+int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p,
+                     const double* xmeans, const double* xscales, const double* R,
+                     int32_t nlv, double* T_out, int64_t ldt);
+
+/* coef(::Plsr; nlv = k) — plskern.jl:207-217: B (p*q, ld = p) = D(1/xscales) R[:,1:k] C[:,1:k]' D(yscales),
+ * intercept (q) = ymeans' - xmeans' B.  k == 0 gives zeros and ymeans.  Tiny; computed on the device
+ * for parity with the predict path. */
+int jcb200_coef(const double* R, const double* C, const double* xmeans, const double* xscales,
+                const double* ymeans, const double* yscales, int64_t p, int64_t q, int32_t k,
+                double* B, double* intercept);
+
+/* predict(::Plsr, X; nlv = k_lo:k_hi) — plskern.jl:226-238: pred_out[i] (m*q, ld = m) =
+ * int_k + X * B_k for k = k_lo + i; the range is contiguous by construction (:229).
+ * One pass over X for the whole range. a = number of LVs of the model (columns of R and C). */
+int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                         const double* R, const double* C, int32_t a,
+                         const double* xmeans, const double* xscales,
+                         const double* ymeans, const double* yscales,
+                         int32_t k_lo, int32_t k_hi, double* const* pred_out);
+
+/* ---- device-pointer entry points (staged fit; one process per GPU shards rows) ------------- */
+
+/* Length (doubles) of the packed partial-Gram buffer [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw 1]:
+ * the single buffer a row-sharded fit all-reduces (sum) across GPUs. */
+int64_t jcb200_packed_len(int64_t p, int64_t q);
+
+/* Strided-sample pivot c (p+q doubles, device): about 1024 evenly spaced rows of the shard.
+ * Multi-GPU: rank 0 computes it and broadcasts, so all partial Grams share one pivot. */
+int jcb200_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy,
+                     int64_t n, int64_t p, int64_t q, double* d_pivot);
+
+/* K1 + K1b: packed (+)= [X-c Y-c]' D [X-c Y-c] upper blocks, weighted column sums and sum(w) of this
+ * row shard; dw == NULL means unit weights.  accumulate != 0 adds to d_packed instead of overwriting
+ * (row chunks streamed from the host). Replaces plskern.jl:117-132 and the per-LV GEMVs :162,:167. */
+int jcb200_gram_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw,
+                    int64_t n, int64_t p, int64_t q, const double* d_pivot, double* d_packed,
+                    int32_t accumulate);
+
+/* K3 + K4 on the (all-reduced) packed buffer: means, scales, X'DX, X'DY, then the LV loop
+ * (plskern.jl:118-126,149-175 in Gram form).  Device outputs: P,R,W p*nlv (ld p), C q*nlv, TT nlv,
+ * xmeans, xscales p, ymeans, yscales q, sumw 1 (the global sum of weights).  nlv already clamped. */
+int jcb200_solve_dev(const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
+                     int32_t nlv, int32_t scal, double* dP, double* dR, double* dW, double* dC,
+                     double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+                     double* dyscales, double* dsumw);
+
+/* K5: dOut (m*ncol, ld = ldo) = bias' + ((X - mu) ./ sigma) * M, M p*ncol (ld = ldm); bias may be NULL.
+ * Scores T (M = R), transform, and single-k predictions (M = R C' D(yscales), bias = ymeans). */
+int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
+                    const double* dsigma, const double* dM, int64_t ldm, int32_t ncol,
+                    const double* dbias, double* dOut, int64_t ldo);
+
+/* K6: predictions for every k in k_lo..k_hi in one pass: dPred holds (k_hi-k_lo+1) consecutive
+ * m*q matrices (ld = m, stride m*q). */
+int jcb200_predict_sweep_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                             const double* dR, const double* dC, int32_t a,
+                             const double* dxmeans, const double* dxscales,
+                             const double* dymeans, const double* dyscales,
+                             int32_t k_lo, int32_t k_hi, double* dPred);
+
+/* K7: in place X[:, j] = (X[:, j] - mu[j]) / sigma[j]  (center! / cscale!, utility.jl:76-81,482-487). */
+int jcb200_center_scale_dev(double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
+                            const double* dsigma);
+
+/* Normalised weights (mweight, utility.jl:715-723): dw_out[i] = (dw ? dw[i] : 1) / *dsumw. */
+int jcb200_weights_dev(const double* dw, int64_t n, const double* dsumw, double* dw_out);
+
+/* K8: counter-based U[0,1) fill: element (i, j) of the n_rows*n_cols shard starting at
+ * global row row0 of an n_global-row matrix gets u(seed, (row0 + i) + j * n_global). */
+int jcb200_fill_uniform_dev(double* d, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed,
+                            int64_t row0, int64_t n_global);
+
+/* Whole single-GPU fit on device-resident inputs (pivot, gram, solve, scores [, write-back]);
+ * dT n*nlv (ld = ldt), dw_out n.  Used by bench.py for the HBM-resident `value`. */
+int jcb200_plskern_fit_dev(double* dX, int64_t ldx, double* dY, int64_t ldy, const double* dw,
+                           int64_t n, int64_t p, int64_t q, int32_t nlv, int32_t scal,
+                           int32_t writeback_xy,
+                           double* dT, int64_t ldt, double* dP, double* dR, double* dW, double* dC,
+                           double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+                           double* dyscales, double* dw_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JCHEMO_B200_H */

@@ -1,0 +1,12 @@
+"""jchemo.jl_b200 — B200-native kernel-PLS path of Jchemo.jl (plskern / transform / coef / predict).
+
+Importable as `jchemo_b200` (see /jchemo_b200.py: the directory name carries a dot).
+The compute lives in libjchemo_b200.so (hand-written sm_100a CUDA behind a C ABI,
+include/jchemo_b200.h); this package is the host-side mirror of the reference's function API.
+"""
+from ._lib import JchemoB200Error, lib, last_timings, LIB_PATH, SIGNATURES  # noqa: F401
+from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict,  # noqa: F401
+                      ensure_mat, CoefResult, PredResult)
+
+__all__ = ["Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "ensure_mat",
+           "JchemoB200Error", "lib", "last_timings"]

@@ -1,0 +1,85 @@
+"""ctypes binding of libjchemo_b200.so — the same C ABI a Julia `ccall` binds (include/jchemo_b200.h).
+
+The library is the product; this module fails loudly when it is missing or cannot be loaded.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjchemo_b200.so")
+
+c_dp = C.POINTER(C.c_double)
+i64, i32 = C.c_int64, C.c_int32
+
+# name -> (restype, argtypes); every symbol include/jchemo_b200.h declares
+SIGNATURES = {
+    "jcb200_version": (C.c_int, []),
+    "jcb200_last_error": (C.c_char_p, []),
+    "jcb200_init": (C.c_int, [C.c_int]),
+    "jcb200_shutdown": (None, []),
+    "jcb200_set_stream": (C.c_int, [C.c_void_p]),
+    "jcb200_last_timings": (C.c_int, [c_dp, C.c_int]),
+    "jcb200_sync_timings": (C.c_int, []),
+    "jcb200_launch_count": (i64, []),
+    "jcb200_host_register": (C.c_int, [C.c_void_p, i64]),
+    "jcb200_host_unregister": (C.c_int, [C.c_void_p]),
+    "jcb200_plskern_fit": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32,
+                                     i32, i32, C.c_void_p, i64] + [C.c_void_p] * 10 +
+                           [C.POINTER(i32)]),
+    "jcb200_transform": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i32,
+                                   C.c_void_p, i64]),
+    "jcb200_coef": (C.c_int, [C.c_void_p] * 6 + [i64, i64, i32, C.c_void_p, C.c_void_p]),
+    "jcb200_predict_sweep": (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.c_void_p, i32] +
+                             [C.c_void_p] * 4 + [i32, i32, C.POINTER(C.c_void_p)]),
+    "jcb200_packed_len": (i64, [i64, i64]),
+    "jcb200_pivot_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
+    "jcb200_gram_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64,
+                                  C.c_void_p, C.c_void_p, i32]),
+    "jcb200_solve_dev": (C.c_int, [C.c_void_p, C.c_void_p, i64, i64, i32, i32] + [C.c_void_p] * 10),
+    "jcb200_xmul_dev": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i64,
+                                  i32, C.c_void_p, C.c_void_p, i64]),
+    "jcb200_predict_sweep_dev": (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.c_void_p, i32] +
+                                 [C.c_void_p] * 4 + [i32, i32, C.c_void_p]),
+    "jcb200_center_scale_dev": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p]),
+    "jcb200_weights_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, C.c_void_p]),
+    "jcb200_fill_uniform_dev": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_uint64, i64, i64]),
+    "jcb200_plskern_fit_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64,
+                                         i32, i32, i32, C.c_void_p, i64] + [C.c_void_p] * 10),
+}
+
+PHASES = ["h2d", "pivot", "gram", "reduce", "finalize", "lvloop", "scores", "writeback", "d2h", "total"]
+
+_lib = None
+
+
+class JchemoB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises if libjchemo_b200.so is absent (build it: python __graft_entry__.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JchemoB200Error(
+                f"{LIB_PATH} not found: build the CUDA library first "
+                "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().jcb200_last_error().decode("utf-8", "replace")
+        raise JchemoB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+def last_timings():
+    buf = (C.c_double * len(PHASES))()
+    n = lib().jcb200_last_timings(buf, len(PHASES))
+    return {PHASES[i]: buf[i] for i in range(n)}

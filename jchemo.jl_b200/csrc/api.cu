@@ -1,0 +1,590 @@
+// C-ABI shim of libjchemo_b200.so: context, error strings, timings and the entry points declared in
+// include/jchemo_b200.h.  No C++ exception crosses the boundary; there is no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "jcb_internal.cuh"
+
+namespace jcb {
+
+static thread_local char tl_error[512] = "";
+static std::mutex g_mutex;
+static Ctx g_ctx;
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+}
+
+Ctx* ctx() { return &g_ctx; }
+
+int ensure(Buf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) {
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return JCB200_ENOMEM;
+    }
+    b.bytes = want;
+    return 0;
+}
+
+void phase_begin(Ctx* c, int ph) {
+    if (!c->ev_used[ph]) cudaEventRecord(c->ev_begin[ph], c->stream);
+}
+void phase_end(Ctx* c, int ph) {
+    cudaEventRecord(c->ev_end[ph], c->stream);
+    c->ev_used[ph] = true;
+}
+static void phases_reset(Ctx* c) {
+    for (int i = 0; i < JCB200_NPHASE; ++i) c->ev_used[i] = false;
+}
+// after the stream has been synchronised
+static void phases_collect(Ctx* c) {
+    for (int i = 0; i < JCB200_NPHASE; ++i) {
+        c->last_ms[i] = 0.0;
+        if (c->ev_used[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_begin[i], c->ev_end[i]) == cudaSuccess)
+                c->last_ms[i] = ms;
+        }
+    }
+}
+
+static int init_locked(int device) {
+    Ctx* c = &g_ctx;
+    if (c->ready && c->device == device) {
+        cudaSetDevice(device);
+        return 0;
+    }
+    if (c->ready) {
+        set_error("already initialised on device %d; call jcb200_shutdown first", c->device);
+        return JCB200_EINVAL;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libjchemo_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return JCB200_ENODEV;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return JCB200_EINVAL;
+    }
+    cudaDeviceProp prop;
+    JCB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d (%s) has compute capability %d.%d; this library is built for sm_100a only",
+                  device, prop.name, prop.major, prop.minor);
+        return JCB200_ENODEV;
+    }
+    JCB_CUDA(cudaSetDevice(device));
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    JCB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    JCB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < JCB200_NPHASE; ++i) {
+        JCB_CUDA(cudaEventCreate(&c->ev_begin[i]));
+        JCB_CUDA(cudaEventCreate(&c->ev_end[i]));
+        c->ev_used[i] = false;
+        c->last_ms[i] = 0.0;
+    }
+    c->ready = true;
+    return 0;
+}
+
+static int ready_locked() {
+    if (g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        return 0;
+    }
+    return init_locked(0);
+}
+
+static void free_buf(Buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+// carve helper for small device outputs
+struct Carver {
+    double* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base((double*)p) {}
+    double* take(size_t n) {
+        double* r = base + off;
+        off += (n + 1) & ~(size_t)1;   // keep 16-byte alignment
+        return r;
+    }
+};
+
+static inline int64_t even_up(int64_t v) { return (v + 1) & ~(int64_t)1; }
+
+// the single-GPU fit on device-resident, aligned inputs
+static int fit_dev_locked(Ctx* c, double* dX, int64_t ldx, double* dY, int64_t ldy, const double* dw,
+                          int64_t n, int64_t p, int64_t q, int nlv, int scal, int writeback,
+                          double* dT, int64_t ldt, double* dP, double* dR, double* dW, double* dC,
+                          double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+                          double* dyscales, double* dw_out, double* d_pivot, double* d_packed,
+                          double* d_sumw) {
+    phase_begin(c, JCB200_T_PIVOT);
+    JCB_TRY(launch_pivot(c, dX, ldx, dY, ldy, n, p, q, d_pivot));
+    phase_end(c, JCB200_T_PIVOT);
+    JCB_TRY(launch_gram(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot, d_packed, 0));
+    JCB_TRY(launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans,
+                         dxscales, dymeans, dyscales, d_sumw));
+    if (nlv > 0)
+        JCB_TRY(launch_xmul(c, dX, ldx, n, p, dxmeans, dxscales, dR, p, nlv, nullptr, dT, ldt));
+    if (dw_out) JCB_TRY(launch_weights(c, dw, n, d_sumw, dw_out));
+    if (writeback) {
+        phase_begin(c, JCB200_T_WRITEBACK);
+        JCB_TRY(launch_center_scale(c, dX, ldx, n, p, dxmeans, dxscales));
+        JCB_TRY(launch_center_scale(c, dY, ldy, n, q, dymeans, dyscales));
+        phase_end(c, JCB200_T_WRITEBACK);
+    }
+    return 0;
+}
+
+}  // namespace jcb
+
+using namespace jcb;
+
+#define API_PROLOGUE()                         \
+    std::lock_guard<std::mutex> lock(g_mutex); \
+    tl_error[0] = 0;                           \
+    {                                          \
+        int _r = ready_locked();               \
+        if (_r != 0) return _r;                \
+    }                                          \
+    Ctx* c = &g_ctx;                           \
+    (void)c
+
+#define ARG_CHECK(cond, msg)      \
+    do {                          \
+        if (!(cond)) {            \
+            set_error("%s", msg); \
+            return JCB200_EINVAL; \
+        }                         \
+    } while (0)
+
+extern "C" {
+
+int jcb200_version(void) { return JCB200_VERSION; }
+
+const char* jcb200_last_error(void) { return tl_error; }
+
+int jcb200_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    tl_error[0] = 0;
+    return init_locked(device);
+}
+
+void jcb200_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    Ctx* c = &g_ctx;
+    if (!c->ready) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_buf(c->partials);
+    free_buf(c->sched_dev);
+    free_buf(c->solve_ws);
+    free_buf(c->xmul_ws);
+    free_buf(c->hX);
+    free_buf(c->hY);
+    free_buf(c->hW);
+    free_buf(c->hT);
+    free_buf(c->hSmall);
+    free_buf(c->hPred);
+    if (c->sched_host) cudaFreeHost(c->sched_host);
+    c->sched_host = nullptr;
+    c->sched_host_bytes = 0;
+    c->sk_p = c->sk_q = c->sk_nst = -1;
+    for (int i = 0; i < JCB200_NPHASE; ++i) {
+        cudaEventDestroy(c->ev_begin[i]);
+        cudaEventDestroy(c->ev_end[i]);
+    }
+    cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    c->ready = false;
+}
+
+int jcb200_set_stream(void* cuda_stream) {
+    API_PROLOGUE();
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+int jcb200_last_timings(double* ms, int cap) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int nph = cap < JCB200_NPHASE ? cap : JCB200_NPHASE;
+    for (int i = 0; i < nph; ++i) ms[i] = g_ctx.last_ms[i];
+    return nph;
+}
+
+int64_t jcb200_launch_count(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return g_launches;
+}
+
+int jcb200_host_register(void* ptr, int64_t bytes) {
+    API_PROLOGUE();
+    JCB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+int jcb200_host_unregister(void* ptr) {
+    API_PROLOGUE();
+    JCB_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
+
+int64_t jcb200_packed_len(int64_t p, int64_t q) { return packed_len(p, q); }
+
+// ------------------------------------------------------------------------------------ device API
+int jcb200_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
+                     int64_t p, int64_t q, double* d_pivot) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dY && d_pivot && n > 0 && p > 0 && q > 0 && ldx >= n && ldy >= n,
+              "pivot_dev: bad argument");
+    return launch_pivot(c, dX, ldx, dY, ldy, n, p, q, d_pivot);
+}
+
+int jcb200_gram_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw,
+                    int64_t n, int64_t p, int64_t q, const double* d_pivot, double* d_packed,
+                    int32_t accumulate) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dY && d_pivot && d_packed && n > 0 && p > 0 && q > 0 && ldx >= n && ldy >= n,
+              "gram_dev: bad argument");
+    phases_reset(c);
+    return launch_gram(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot, d_packed, accumulate);
+}
+
+int jcb200_solve_dev(const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
+                     int32_t nlv, int32_t scal, double* dP, double* dR, double* dW, double* dC,
+                     double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+                     double* dyscales, double* dsumw) {
+    API_PROLOGUE();
+    ARG_CHECK(d_packed && d_pivot && p > 0 && q > 0 && nlv >= 0 && dxmeans && dxscales && dymeans &&
+                  dyscales && dsumw,
+              "solve_dev: bad argument");
+    ARG_CHECK(nlv == 0 || (dP && dR && dW && dC && dTT), "solve_dev: NULL output");
+    return launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans, dxscales,
+                        dymeans, dyscales, dsumw);
+}
+
+int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
+                    const double* dsigma, const double* dM, int64_t ldm, int32_t ncol,
+                    const double* dbias, double* dOut, int64_t ldo) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dmu && dM && dOut && m > 0 && p > 0 && ncol >= 0 && ldx >= m && ldm >= p &&
+                  ldo >= m,
+              "xmul_dev: bad argument");
+    return launch_xmul(c, dX, ldx, m, p, dmu, dsigma, dM, ldm, ncol, dbias, dOut, ldo);
+}
+
+int jcb200_predict_sweep_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                             const double* dR, const double* dC, int32_t a, const double* dxmeans,
+                             const double* dxscales, const double* dymeans, const double* dyscales,
+                             int32_t k_lo, int32_t k_hi, double* dPred) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dxmeans && dxscales && dymeans && dyscales && dPred && m > 0 && p > 0 && q > 0 &&
+                  ldx >= m && a >= 0 && k_lo >= 0 && k_hi >= k_lo && k_hi <= a,
+              "predict_sweep_dev: bad argument");
+    ARG_CHECK(a == 0 || (dR && dC), "predict_sweep_dev: NULL model");
+    return launch_predict_sweep(c, dX, ldx, m, p, q, dR, dC, a, dxmeans, dxscales, dymeans, dyscales,
+                                k_lo, k_hi, dPred);
+}
+
+int jcb200_center_scale_dev(double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
+                            const double* dsigma) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dmu && n > 0 && p > 0 && ldx >= n, "center_scale_dev: bad argument");
+    return launch_center_scale(c, dX, ldx, n, p, dmu, dsigma);
+}
+
+int jcb200_weights_dev(const double* dw, int64_t n, const double* dsumw, double* dw_out) {
+    API_PROLOGUE();
+    ARG_CHECK(dsumw && dw_out && n > 0, "weights_dev: bad argument");
+    return launch_weights(c, dw, n, dsumw, dw_out);
+}
+
+int jcb200_fill_uniform_dev(double* d, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed,
+                            int64_t row0, int64_t n_global) {
+    API_PROLOGUE();
+    ARG_CHECK(d && ld >= n_rows && n_rows > 0 && n_cols > 0 && n_global >= n_rows,
+              "fill_uniform_dev: bad argument");
+    return launch_fill_uniform(c, d, ld, n_rows, n_cols, seed, row0, n_global);
+}
+
+int jcb200_plskern_fit_dev(double* dX, int64_t ldx, double* dY, int64_t ldy, const double* dw,
+                           int64_t n, int64_t p, int64_t q, int32_t nlv, int32_t scal,
+                           int32_t writeback_xy, double* dT, int64_t ldt, double* dP, double* dR,
+                           double* dW, double* dC, double* dTT, double* dxmeans, double* dxscales,
+                           double* dymeans, double* dyscales, double* dw_out) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dY && n > 0 && p > 0 && q > 0 && nlv >= 0 && ldx >= n && ldy >= n,
+              "plskern_fit_dev: bad argument");
+    ARG_CHECK(dxmeans && dxscales && dymeans && dyscales, "plskern_fit_dev: NULL output");
+    if (nlv > n) nlv = (int32_t)n;
+    if (nlv > p) nlv = (int32_t)p;
+    ARG_CHECK(nlv == 0 || (dT && dP && dR && dW && dC && dTT && ldt >= n),
+              "plskern_fit_dev: NULL output");
+    JCB_TRY(ensure(c->hSmall, (size_t)(packed_len(p, q) + (p + q) + 16) * 8));
+    Carver cv(c->hSmall.p);
+    double* d_packed = cv.take(packed_len(p, q));
+    double* d_pivot = cv.take(p + q);
+    double* d_sumw = cv.take(2);
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    JCB_TRY(fit_dev_locked(c, dX, ldx, dY, ldy, dw, n, p, q, nlv, scal, writeback_xy, dT, ldt, dP, dR,
+                           dW, dC, dTT, dxmeans, dxscales, dymeans, dyscales, dw_out, d_pivot, d_packed,
+                           d_sumw));
+    phase_end(c, JCB200_T_TOTAL);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ host API
+int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const double* w, int64_t n,
+                       int64_t p, int64_t q, int32_t nlv, int32_t scal, int32_t writeback_xy,
+                       double* T, int64_t ldt, double* P, double* R, double* W, double* C, double* TT,
+                       double* xmeans, double* xscales, double* ymeans, double* yscales,
+                       double* w_out, int32_t* nlv_out) {
+    API_PROLOGUE();
+    ARG_CHECK(X && Y, "plskern_fit: X and Y are required");
+    ARG_CHECK(n > 0 && p > 0 && q > 0, "plskern_fit: n, p, q must be positive");
+    ARG_CHECK(nlv >= 0, "plskern_fit: nlv must be >= 0");
+    ARG_CHECK(ldx >= n && ldy >= n, "plskern_fit: leading dimension smaller than n");
+    ARG_CHECK(xmeans && xscales && ymeans && yscales && w_out, "plskern_fit: NULL output");
+    if (nlv > n) nlv = (int32_t)n;                      // nlv = min(n, p, nlv), plskern.jl:116
+    if (nlv > p) nlv = (int32_t)p;
+    if (nlv_out) *nlv_out = nlv;
+    ARG_CHECK(nlv == 0 || (T && P && R && W && C && TT && ldt >= n), "plskern_fit: NULL output");
+
+    const int64_t ld = even_up(n);
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
+    JCB_TRY(ensure(c->hT, (size_t)ld * (nlv > 0 ? nlv : 1) * 8));
+    const size_t small_doubles = (size_t)packed_len(p, q) + (p + q) + 16 + 3 * (size_t)p * nlv +
+                                 (size_t)q * nlv + nlv + 2 * (p + q) + 64;
+    JCB_TRY(ensure(c->hSmall, small_doubles * 8));
+    double* dX = (double*)c->hX.p;
+    double* dY = (double*)c->hY.p;
+    double* dw = w ? (double*)c->hW.p : nullptr;
+    double* dwout = (double*)c->hW.p + ld;
+    double* dT = (double*)c->hT.p;
+    Carver cv(c->hSmall.p);
+    double* d_packed = cv.take(packed_len(p, q));
+    double* d_pivot = cv.take(p + q);
+    double* d_sumw = cv.take(2);
+    double* dP = cv.take((size_t)p * nlv);
+    double* dR = cv.take((size_t)p * nlv);
+    double* dW = cv.take((size_t)p * nlv);
+    double* dC = cv.take((size_t)q * nlv);
+    double* dTT = cv.take(nlv);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dym = cv.take(q);
+    double* dys = cv.take(q);
+
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, n * 8, p, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpy2DAsync(dY, ld * 8, Y, ldy * 8, n * 8, q, cudaMemcpyHostToDevice, st));
+    if (w) JCB_CUDA(cudaMemcpyAsync(dw, w, n * 8, cudaMemcpyHostToDevice, st));
+    phase_end(c, JCB200_T_H2D);
+
+    JCB_TRY(fit_dev_locked(c, dX, ld, dY, ld, dw, n, p, q, nlv, scal, writeback_xy, dT, ld, dP, dR,
+                           dW, dC, dTT, dxm, dxs, dym, dys, dwout, d_pivot, d_packed, d_sumw));
+
+    phase_begin(c, JCB200_T_D2H);
+    if (nlv > 0) {
+        JCB_CUDA(cudaMemcpy2DAsync(T, ldt * 8, dT, ld * 8, n * 8, nlv, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(W, dW, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(C, dC, (size_t)q * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(TT, dTT, (size_t)nlv * 8, cudaMemcpyDeviceToHost, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(xmeans, dxm, p * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(w_out, dwout, n * 8, cudaMemcpyDeviceToHost, st));
+    if (writeback_xy) {
+        JCB_CUDA(cudaMemcpy2DAsync(X, ldx * 8, dX, ld * 8, n * 8, p, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, dY, ld * 8, n * 8, q, cudaMemcpyDeviceToHost, st));
+    }
+    phase_end(c, JCB200_T_D2H);
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    return 0;
+}
+
+int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const double* xmeans,
+                     const double* xscales, const double* R, int32_t nlv, double* T_out,
+                     int64_t ldt) {
+    API_PROLOGUE();
+    ARG_CHECK(X && xmeans && xscales && m > 0 && p > 0 && nlv >= 0 && ldx >= m,
+              "transform: bad argument");
+    if (nlv == 0) return 0;
+    ARG_CHECK(R && T_out && ldt >= m, "transform: NULL R or output");
+    const int64_t ld = even_up(m);
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hT, (size_t)ld * nlv * 8));
+    JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + (size_t)p * nlv + 16) * 8));
+    double* dX = (double*)c->hX.p;
+    double* dT = (double*)c->hT.p;
+    Carver cv(c->hSmall.p);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dR = cv.take((size_t)p * nlv);
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, m * 8, p, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
+    phase_end(c, JCB200_T_H2D);
+    JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
+    phase_begin(c, JCB200_T_D2H);
+    JCB_CUDA(cudaMemcpy2DAsync(T_out, ldt * 8, dT, ld * 8, m * 8, nlv, cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_D2H);
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    return 0;
+}
+
+int jcb200_coef(const double* R, const double* C, const double* xmeans, const double* xscales,
+                const double* ymeans, const double* yscales, int64_t p, int64_t q, int32_t k,
+                double* B, double* intercept) {
+    API_PROLOGUE();
+    ARG_CHECK(xmeans && xscales && ymeans && yscales && B && intercept && p > 0 && q > 0 && k >= 0,
+              "coef: bad argument");
+    ARG_CHECK(k == 0 || (R && C), "coef: NULL R or C");
+    const size_t nd = (size_t)p * k + (size_t)q * k + 2 * (p + q) + (size_t)p * q + q + 64;
+    JCB_TRY(ensure(c->hSmall, nd * 8));
+    Carver cv(c->hSmall.p);
+    double* dR = cv.take((size_t)p * k);
+    double* dC = cv.take((size_t)q * k);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dym = cv.take(q);
+    double* dys = cv.take(q);
+    double* dB = cv.take((size_t)p * q);
+    double* dint = cv.take(q);
+    cudaStream_t st = c->stream;
+    if (k > 0) {
+        JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * k * 8, cudaMemcpyHostToDevice, st));
+        JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * k * 8, cudaMemcpyHostToDevice, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dym, ymeans, q * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dys, yscales, q * 8, cudaMemcpyHostToDevice, st));
+    JCB_TRY(launch_coef(c, dR, dC, dxm, dxs, dym, dys, p, q, k, dB, dint));
+    JCB_CUDA(cudaMemcpyAsync(B, dB, (size_t)p * q * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(intercept, dint, q * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                         const double* R, const double* C, int32_t a, const double* xmeans,
+                         const double* xscales, const double* ymeans, const double* yscales,
+                         int32_t k_lo, int32_t k_hi, double* const* pred_out) {
+    API_PROLOGUE();
+    ARG_CHECK(X && xmeans && xscales && ymeans && yscales && pred_out && m > 0 && p > 0 && q > 0 &&
+                  ldx >= m && a >= 0 && k_lo >= 0 && k_hi >= k_lo && k_hi <= a,
+              "predict_sweep: bad argument");
+    ARG_CHECK(a == 0 || (R && C), "predict_sweep: NULL model");
+    const int nk = k_hi - k_lo + 1;
+    for (int i = 0; i < nk; ++i) ARG_CHECK(pred_out[i], "predict_sweep: NULL output matrix");
+    const int64_t ld = even_up(m);
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hPred, (size_t)nk * m * q * 8));
+    const size_t nd = (size_t)p * a + (size_t)q * a + 2 * (p + q) + (size_t)p * q + q + 64;
+    JCB_TRY(ensure(c->hSmall, nd * 8));
+    double* dX = (double*)c->hX.p;
+    double* dPred = (double*)c->hPred.p;
+    Carver cv(c->hSmall.p);
+    double* dR = cv.take((size_t)p * a);
+    double* dC = cv.take((size_t)q * a);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dym = cv.take(q);
+    double* dys = cv.take(q);
+    double* dB = cv.take((size_t)p * q);
+    double* dint = cv.take(q);
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, m * 8, p, cudaMemcpyHostToDevice, st));
+    if (a > 0) {
+        JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * a * 8, cudaMemcpyHostToDevice, st));
+        JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * a * 8, cudaMemcpyHostToDevice, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dym, ymeans, q * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dys, yscales, q * 8, cudaMemcpyHostToDevice, st));
+    phase_end(c, JCB200_T_H2D);
+    if (nk == 1 && k_lo > 0) {
+        // single k: the reference's own arithmetic, pred = int + X B (plskern.jl:233-234),
+        // as ymeans + (X - xmeans) B
+        JCB_TRY(launch_coef(c, dR, dC, dxm, dxs, dym, dys, p, q, k_lo, dB, dint));
+        JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, nullptr, dB, p, (int)q, dym, dPred, m));
+    } else {
+        JCB_TRY(launch_predict_sweep(c, dX, ld, m, p, q, dR, dC, a, dxm, dxs, dym, dys, k_lo, k_hi,
+                                     dPred));
+    }
+    phase_begin(c, JCB200_T_D2H);
+    for (int i = 0; i < nk; ++i)
+        JCB_CUDA(cudaMemcpyAsync(pred_out[i], dPred + (size_t)i * m * q, (size_t)m * q * 8,
+                                 cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_D2H);
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    return 0;
+}
+
+/* collect timings of the device-pointer entry points (call after synchronising the stream) */
+int jcb200_sync_timings(void) {
+    API_PROLOGUE();
+    JCB_CUDA(cudaStreamSynchronize(c->stream));
+    phases_collect(c);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// Internal declarations shared by the kernels and the C-ABI shim of libjchemo_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/jchemo_b200.h"
+
+namespace jcb {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;   // kernels launched by this library (guarded by the API mutex)
+
+#define JCB_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            jcb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                      \
+            return (int)_e;                                                                \
+        }                                                                                  \
+    } while (0)
+
+#define JCB_LAUNCH_CHECK()                                                                 \
+    do {                                                                                   \
+        jcb::g_launches++;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            jcb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),     \
+                           __FILE__, __LINE__);                                            \
+            return (int)_e;                                                                \
+        }                                                                                  \
+    } while (0)
+
+#define JCB_TRY(call)                 \
+    do {                              \
+        int _r = (call);              \
+        if (_r != 0) return _r;       \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+struct Buf {            // grow-only device scratch
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream = nullptr;   // stream in use (own_stream or external)
+    // K1 scratch
+    Buf partials;        // split-K partial units
+    Buf sched_dev;       // device copy of the schedule
+    void* sched_host = nullptr;  // pinned staging for the schedule
+    size_t sched_host_bytes = 0;
+    // schedule cache key
+    int64_t sk_p = -1, sk_q = -1, sk_nst = -1;
+    int sk_ngroups = 0, sk_nsegs = 0;
+    // solve / xmul scratch
+    Buf solve_ws;
+    Buf xmul_ws;
+    // general scratch for the host-pointer API
+    Buf hX, hY, hW, hT, hSmall, hPred;
+    // timing
+    cudaEvent_t ev_begin[JCB200_NPHASE], ev_end[JCB200_NPHASE];
+    bool ev_used[JCB200_NPHASE];
+    double last_ms[JCB200_NPHASE];
+};
+
+Ctx* ctx();                               // the process-wide context (API mutex must be held)
+int ensure(Buf& b, size_t bytes);         // grow-only cudaMalloc
+void phase_begin(Ctx* c, int ph);
+void phase_end(Ctx* c, int ph);
+
+// ---------------------------------------------------------------- kernel launchers
+int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
+                 int64_t p, int64_t q, double* d_pivot);
+int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
+                const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
+                double* d_packed, int accumulate);
+int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
+                 int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
+                 double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
+                 double* dsumw);
+int launch_xmul(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
+                const double* dsigma, const double* dM, int64_t ldm, int ncol, const double* dbias,
+                double* dOut, int64_t ldo);
+int launch_predict_sweep(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                         const double* dR, const double* dC, int a, const double* dxmeans,
+                         const double* dxscales, const double* dymeans, const double* dyscales,
+                         int k_lo, int k_hi, double* dPred);
+int launch_center_scale(Ctx* c, double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
+                        const double* dsigma);
+int launch_weights(Ctx* c, const double* dw, int64_t n, const double* dsumw, double* dw_out);
+int launch_fill_uniform(Ctx* c, double* d, int64_t ld, int64_t n_rows, int64_t n_cols,
+                        uint64_t seed, int64_t row0, int64_t n_global);
+int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmeans,
+                const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
+                int64_t q, int k, double* dB, double* dint);
+
+inline int64_t packed_len(int64_t p, int64_t q) { return p * p + p * q + q + p + q + 1; }
+// offsets into the packed buffer
+inline int64_t off_gxy(int64_t p, int64_t q) { return p * p; }
+inline int64_t off_gyy(int64_t p, int64_t q) { return p * p + p * q; }
+inline int64_t off_sx(int64_t p, int64_t q) { return p * p + p * q + q; }
+inline int64_t off_sy(int64_t p, int64_t q) { return p * p + p * q + q + p; }
+inline int64_t off_sw(int64_t p, int64_t q) { return p * p + p * q + q + p + q; }
+
+}  // namespace jcb
+
+// ---------------------------------------------------------------- device PTX helpers
+#ifdef __CUDACC__
+namespace jcb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 2-D tiled TMA load: coordinates (c0 = innermost/row, c1 = column)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+        "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* map, int c0,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+        "{%3}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (no tensor map): 16-byte aligned, size multiple of 16
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes,
+                                          uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col); lowers to DMMA.8x8x4 on sm_100a.
+// lane = 4*g + kk holds A[g][kk], B[kk][g], and C[g][2*kk], C[g][2*kk+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+}  // namespace jcb
+#endif

@@ -1,0 +1,671 @@
+// K1 — fused weight / centre + FP64 tensor-core SYRK/GEMM:  G = [X-c Y-c]' D [X-c Y-c]
+// (upper 32x32 units only), weighted column sums and sum(w), for one row shard.
+//
+// Replaces, in Gram form, the reference's preamble and per-LV GEMVs:
+//   mweight/colmean/center!/cscale! + X'(D Y)      /root/reference/src/plskern.jl:117-132
+//   mul!(t, X, r), mul!(zp, X', dt) per LV          /root/reference/src/plskern.jl:162,167
+//
+// Design (B200, sm_100a):
+//  * X, Y are column-major (rows contiguous) so the contraction dimension K = rows is contiguous for
+//    both operands.  The augmented column space is cut into 32-column blocks (X blocks, then Y blocks);
+//    a 32x32 output "unit" (block_a, block_b) is owned by one warp: 16 DMMA.8x8x4 accumulators.
+//  * A CTA (16 consumer warps + 1 TMA producer warp) works on a "group": up to 8 column blocks staged
+//    per pipeline stage and up to 16 units on them (an off-diagonal 128x128 super-tile, or a diagonal
+//    super-tile + the X'Y / Y'Y units).  Diagonal units skip the 8x8 blocks below the diagonal.
+//  * Rows are streamed in stages of KT = 40 rows by 2-D TMA (FP64 tensor map, zero fill out of
+//    bounds) into a [column][KT] shared-memory tile; KT = 40 makes the 128-bit fragment loads
+//    bank-conflict free.  Full/empty mbarriers form a 2-stage ring.
+//  * Centring (x - c, c = strided-sample pivot) and weighting happen on the fragments in registers;
+//    the exact correction G - delta delta' is applied in K3.  Zero-filled tail rows get weight 0.
+//  * Weighted stream-K: the (group, stage) space is cut into equal-cost contiguous pieces, one per SM,
+//    so every SM is busy for the same time; each piece writes its partial units to a workspace and
+//    K1b sums them in a fixed order (deterministic, no atomics).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "jcb_internal.cuh"
+
+namespace jcb {
+
+constexpr int KT = 40;                 // rows per pipeline stage
+constexpr int CB = 32;                 // columns per block
+constexpr int MAXSLOT = 8;             // column blocks staged per stage
+constexpr int NSTAGE = 2;              // pipeline depth
+constexpr int NCW = 16;                // consumer warps per CTA
+constexpr int K1_THREADS = NCW * 32;    // warp 0 / lane 0 doubles as the TMA producer
+constexpr int UNIT_STRIDE = 1088;      // doubles per partial unit: 1024 G + 32 column sums + sum(w) + pad
+constexpr int SLOT_DOUBLES = CB * KT;  // 1280
+constexpr int STAGE_BYTES = MAXSLOT * SLOT_DOUBLES * 8 + 512;  // data + weight tile (KT doubles, padded)
+constexpr int K1_SMEM = NSTAGE * STAGE_BYTES + MAXSLOT * CB * 8 + 64;   // + pivot tile + mbarriers
+
+struct UnitDesc {
+    int8_t sa, sb;      // slots of the A (rows of G) and B (columns of G) blocks
+    int8_t kind;        // 0 idle, 1 full, 2 diagonal (skip 8x8 blocks with mb > nb)
+    int8_t mbc, nbc;    // active 8-blocks in A / B (edge blocks are narrower)
+    int8_t sums;        // bit0: accumulate column sums of the B block, bit1: accumulate sum(w)
+    int8_t pad[2];
+};
+struct GroupDesc {
+    int32_t nslots;
+    int32_t blk[MAXSLOT];
+    UnitDesc unit[NCW];
+};
+struct SegDesc {
+    int32_t group, s0, s1, pad;
+};
+
+struct GramParams {
+    const GroupDesc* groups;
+    const SegDesc* segs;
+    const int32_t* cta_seg;   // [ncta + 1]
+    const double* pivot;      // p + q
+    double* partials;         // nsegs * NCW * UNIT_STRIDE
+    int64_t n;
+    int32_t p, q, nbx;
+    int32_t weighted;
+};
+
+// ------------------------------------------------------------------------------------------ kernel
+template <bool WEIGHTED>
+__device__ __forceinline__ void compute_stage(const double* __restrict__ tA,
+                                              const double* __restrict__ tB,
+                                              const double* __restrict__ wt,
+                                              const double* __restrict__ pA,
+                                              const double* __restrict__ pB, int g, int kk,
+                                              double (&acc)[4][4][2], double (&bsum)[4],
+                                              double& wsum, const uint32_t mask, const int sums,
+                                              bool masked, int rows_valid) {
+    // mask bit (mb*4+nb) set <=> this 8x8 block of the unit is computed
+#pragma unroll 1
+    for (int k8 = 0; k8 < KT / 8; ++k8) {
+        const int ko = k8 * 8 + 2 * kk;
+        double2 a[4];
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            a[mb] = *reinterpret_cast<const double2*>(tA + (mb * 8 + g) * KT + ko);
+            const double c = pA[mb * 8 + g];
+            a[mb].x -= c;
+            a[mb].y -= c;
+        }
+        double2 w2 = make_double2(1.0, 1.0);
+        if (WEIGHTED) {
+            w2 = *reinterpret_cast<const double2*>(wt + ko);
+        } else if (masked) {
+            w2.x = (ko < rows_valid) ? 1.0 : 0.0;
+            w2.y = (ko + 1 < rows_valid) ? 1.0 : 0.0;
+        }
+        if (sums & 2) wsum += w2.x + w2.y;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            double2 b = *reinterpret_cast<const double2*>(tB + (nb * 8 + g) * KT + ko);
+            const double c = pB[nb * 8 + g];
+            if (WEIGHTED || masked) {
+                b.x = (b.x - c) * w2.x;
+                b.y = (b.y - c) * w2.y;
+            } else {
+                b.x -= c;
+                b.y -= c;
+            }
+            if (sums & 1) bsum[nb] += b.x + b.y;
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                if (mask & (1u << (mb * 4 + nb))) {
+                    dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b.x);
+                    dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b.y);
+                }
+            }
+        }
+    }
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+            const __grid_constant__ CUtensorMap mapW, const GramParams prm) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    double* piv_s = reinterpret_cast<double*>(smem + NSTAGE * STAGE_BYTES);   // [MAXSLOT][CB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(piv_s + MAXSLOT * CB);
+    uint64_t* empty = full + NSTAGE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int seg_begin = prm.cta_seg[blockIdx.x], seg_end = prm.cta_seg[blockIdx.x + 1];
+    const int64_t n = prm.n;
+    const bool producer = (threadIdx.x == 0);
+
+    // ---- producer cursor (thread 0 only): next (segment, stage) to request, and its ring position
+    int p_sg = seg_begin, p_st = 0;
+    uint32_t p_it = 0;
+    if (producer && p_sg < seg_end) p_st = prm.segs[p_sg].s0;
+    auto produce_one = [&]() {
+        // requests one stage if any is left; waits for the ring slot to be free first
+        if (p_sg >= seg_end) return;
+        const SegDesc seg = prm.segs[p_sg];
+        const GroupDesc* gd = &prm.groups[seg.group];
+        const int nslots = gd->nslots;
+        const int buf = p_it % NSTAGE;
+        const uint32_t ph = (p_it / NSTAGE) & 1;
+        mbar_wait(&empty[buf], ph ^ 1);
+        const uint32_t bytes = nslots * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
+        mbar_arrive_expect_tx(&full[buf], bytes);
+        unsigned char* base = smem + buf * STAGE_BYTES;
+        const int row0 = p_st * KT;
+        for (int s = 0; s < nslots; ++s) {
+            const int b = gd->blk[s];
+            const bool isy = b >= prm.nbx;
+            tma_load_2d(base + s * SLOT_DOUBLES * 8, isy ? &mapY : &mapX, row0,
+                        (isy ? b - prm.nbx : b) * CB, &full[buf]);
+        }
+        if (WEIGHTED) tma_load_1d(base + MAXSLOT * SLOT_DOUBLES * 8, &mapW, row0, &full[buf]);
+        ++p_it;
+        if (++p_st >= seg.s1) {
+            ++p_sg;
+            if (p_sg < seg_end) p_st = prm.segs[p_sg].s0;
+        }
+    };
+    if (producer)
+        for (int s = 0; s < NSTAGE; ++s) produce_one();
+
+    // ---- consumers (all 16 warps)
+    const int g = lane >> 2, kk = lane & 3;
+    uint32_t it = 0;  // stages consumed by this CTA so far (ring position)
+    for (int sg = seg_begin; sg < seg_end; ++sg) {
+        const SegDesc seg = prm.segs[sg];
+        const GroupDesc* gd = &prm.groups[seg.group];
+        const UnitDesc u = gd->unit[warp];
+        // pivots of this group's staged columns (0 for padding columns: TMA zero-fills them)
+        __syncthreads();   // previous segment's readers of piv_s are done
+        for (int e = threadIdx.x; e < MAXSLOT * CB; e += K1_THREADS) {
+            const int s = e / CB, cidx = e - s * CB;
+            double v = 0.0;
+            if (s < gd->nslots) {
+                const int b = gd->blk[s];
+                if (b >= prm.nbx) {
+                    const int col = (b - prm.nbx) * CB + cidx;
+                    if (col < prm.q) v = prm.pivot[prm.p + col];
+                } else {
+                    const int col = b * CB + cidx;
+                    if (col < prm.p) v = prm.pivot[col];
+                }
+            }
+            piv_s[e] = v;
+        }
+        __syncthreads();
+        uint32_t mask = 0;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+                if (u.kind && mb < u.mbc && nb < u.nbc && !(u.kind == 2 && mb > nb))
+                    mask |= 1u << (mb * 4 + nb);
+        double acc[4][4][2];
+        double bsum[4];
+        double wsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bsum[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+        for (int st = seg.s0; st < seg.s1; ++st, ++it) {
+            const int buf = it % NSTAGE;
+            const uint32_t ph = (it / NSTAGE) & 1;
+            mbar_wait(&full[buf], ph);
+            if (u.kind) {
+                const double* base = reinterpret_cast<const double*>(smem + buf * STAGE_BYTES);
+                const int64_t rows_left = n - (int64_t)st * KT;
+                const bool masked = rows_left < KT;
+                compute_stage<WEIGHTED>(base + u.sa * SLOT_DOUBLES, base + u.sb * SLOT_DOUBLES,
+                                        base + MAXSLOT * SLOT_DOUBLES, piv_s + u.sa * CB,
+                                        piv_s + u.sb * CB, g, kk, acc, bsum, wsum, mask, u.sums,
+                                        masked, masked ? (int)rows_left : KT);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[buf]);
+            if (producer) produce_one();   // refill this ring slot once all warps have released it
+            __syncwarp();
+        }
+        // ---- write this warp's partial unit (fragment order; K1b knows the layout)
+        if (u.kind) {
+            double* out = prm.partials + ((int64_t)sg * NCW + warp) * UNIT_STRIDE;
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb)
+                    *reinterpret_cast<double2*>(out + ((mb * 4 + nb) * 32 + lane) * 2) =
+                        make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            if (u.sums) {
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    double v = bsum[nb];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (kk == 0) out[1024 + nb * 8 + g] = v;
+                }
+                double v = wsum;
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (lane == 0) out[1056] = v;
+            }
+        }
+    }
+}
+
+// K1b — ordered split-K reduce of the partial units into the packed buffer
+// [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw].  One block per (group, warp-unit).
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restrict__ group_seg,
+                   const double* __restrict__ partials, double* __restrict__ packed, int p, int q,
+                   int nbx, int accumulate) {
+    const int gi = blockIdx.x / NCW, wu = blockIdx.x % NCW;
+    const GroupDesc* gd = &groups[gi];
+    const UnitDesc u = gd->unit[wu];
+    if (!u.kind) return;
+    const int sbeg = group_seg[gi], send = group_seg[gi + 1];
+    const int ba = gd->blk[u.sa], bb = gd->blk[u.sb];
+    const bool ay = ba >= nbx, by = bb >= nbx;
+    const int rowbase = (ay ? ba - nbx : ba) * CB, colbase = (by ? bb - nbx : bb) * CB;
+    const int64_t P = p, Q = q;
+    double* gxx = packed;
+    double* gxy = packed + P * P;
+    double* gyy = gxy + P * Q;
+    double* sx = gyy + Q;
+    double* sy = sx + P;
+    double* sw = sy + Q;
+    const int nelem = 1024 + ((u.sums & 1) ? 32 : 0);
+    for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+        double s = 0.0;
+        for (int sg = sbeg; sg < send; ++sg)
+            s += partials[((int64_t)sg * NCW + wu) * UNIT_STRIDE + e];
+        double* dst = nullptr;
+        if (e < 1024) {
+            const int blk = e >> 6, ln = (e >> 1) & 31, half = e & 1;
+            const int mb = blk >> 2, nb = blk & 3;
+            if (u.kind == 2 && mb > nb) continue;
+            const int row = rowbase + mb * 8 + (ln >> 2), col = colbase + nb * 8 + (ln & 3) * 2 + half;
+            if (!ay && !by) {
+                if (row < p && col < p) dst = gxx + row + (int64_t)col * P;
+            } else if (!ay && by) {
+                if (row < p && col < q) dst = gxy + row + (int64_t)col * P;
+            } else if (ay && by) {
+                if (row == col && row < q) dst = gyy + row;
+            }
+        } else {
+            const int col = colbase + (e - 1024);
+            if (!by) {
+                if (col < p) dst = sx + col;
+            } else {
+                if (col < q) dst = sy + col;
+            }
+        }
+        if (dst) *dst = (accumulate ? *dst : 0.0) + s;
+    }
+    if ((u.sums & 2) && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int sg = sbeg; sg < send; ++sg)
+            s += partials[((int64_t)sg * NCW + wu) * UNIT_STRIDE + 1056];
+        *sw = (accumulate ? *sw : 0.0) + s;
+    }
+}
+
+// Strided-sample pivot: mean of ~1024 evenly spaced rows per column.  One warp per column.
+__global__ void pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y,
+                             int64_t ldy, int64_t n, int p, int q, double* __restrict__ pivot) {
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (col >= p + q) return;
+    const double* src = col < p ? X + (int64_t)col * ldx : Y + (int64_t)(col - p) * ldy;
+    const int64_t ns = n < 1024 ? n : 1024;
+    const int64_t stride = n / ns;
+    double s = 0.0;
+    for (int64_t t = lane; t < ns; t += 32) s += src[t * stride];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) pivot[col] = s / (double)ns;
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map_2d(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld,
+                       int box_rows, int box_cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return JCB200_ENODEV;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(2d) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
+                  (int)r, (long long)rows, (long long)cols, (long long)ld);
+        return JCB200_EINVAL;
+    }
+    return 0;
+}
+
+static int make_map_1d(CUtensorMap* map, const double* base, int64_t len, int box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return JCB200_ENODEV;
+    }
+    cuuint64_t dims[1] = {(cuuint64_t)len};
+    cuuint64_t strides[1] = {0};
+    cuuint32_t boxd[1] = {(cuuint32_t)box};
+    cuuint32_t estr[1] = {1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 1, const_cast<double*>(base), dims,
+                     strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(1d) failed with CUresult %d", (int)r);
+        return JCB200_EINVAL;
+    }
+    return 0;
+}
+
+// Cost of a unit in DMMA pairs per k8-step, used to balance SMSPs and SMs.
+static int unit_cost(const UnitDesc& u) {
+    int c = 0;
+    for (int mb = 0; mb < u.mbc; ++mb)
+        for (int nb = 0; nb < u.nbc; ++nb)
+            if (!(u.kind == 2 && mb > nb)) ++c;
+    return c;
+}
+
+struct Schedule {
+    std::vector<GroupDesc> groups;
+    std::vector<double> gcost;
+    std::vector<SegDesc> segs;
+    std::vector<int32_t> cta_seg;    // ncta + 1
+    std::vector<int32_t> group_seg;  // ngroups + 1
+};
+
+// Fixed per-stage overhead of a group in the same units as unit_cost (fragment transforms, barrier).
+static double g_stage_overhead = 1.5;
+
+static void build_groups(int64_t p, int64_t q, Schedule& S) {
+    const int nbx = (int)((p + CB - 1) / CB), nby = (int)((q + CB - 1) / CB);
+    auto blk_cols = [&](int b) {  // real columns in block b
+        if (b < nbx) return (int)std::min<int64_t>(CB, p - (int64_t)b * CB);
+        return (int)std::min<int64_t>(CB, q - (int64_t)(b - nbx) * CB);
+    };
+    auto nb8 = [&](int b) { return (blk_cols(b) + 7) / 8; };
+    const int ns = (nbx + 3) / 4;
+    struct RawUnit { int ba, bb, kind, sums; };
+    auto emit = [&](const std::vector<int>& slots, std::vector<RawUnit>& units) {
+        // split into groups of at most NCW units that share the slot list
+        for (size_t u0 = 0; u0 < units.size(); u0 += NCW) {
+            GroupDesc gd;
+            memset(&gd, 0, sizeof(gd));
+            gd.nslots = (int)slots.size();
+            for (size_t s = 0; s < slots.size(); ++s) gd.blk[s] = slots[s];
+            std::vector<UnitDesc> us;
+            for (size_t k = u0; k < std::min(units.size(), u0 + NCW); ++k) {
+                UnitDesc u;
+                memset(&u, 0, sizeof(u));
+                u.sa = (int8_t)(std::find(slots.begin(), slots.end(), units[k].ba) - slots.begin());
+                u.sb = (int8_t)(std::find(slots.begin(), slots.end(), units[k].bb) - slots.begin());
+                u.kind = (int8_t)units[k].kind;
+                u.mbc = (int8_t)nb8(units[k].ba);
+                u.nbc = (int8_t)nb8(units[k].bb);
+                u.sums = (int8_t)units[k].sums;
+                us.push_back(u);
+            }
+            // LPT assignment of units to warps so that the 4 SMSPs (warp % 4) carry equal DMMA load
+            std::sort(us.begin(), us.end(),
+                      [](const UnitDesc& a, const UnitDesc& b) { return unit_cost(a) > unit_cost(b); });
+            int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            for (const UnitDesc& u : us) {
+                int best = -1;
+                for (int s = 0; s < 4; ++s)
+                    if (used[s] < NCW / 4 && (best < 0 || load[s] < load[best])) best = s;
+                gd.unit[used[best] * 4 + best] = u;
+                used[best]++;
+                load[best] += unit_cost(u);
+            }
+            int mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+            S.groups.push_back(gd);
+            S.gcost.push_back((double)mx + g_stage_overhead);
+        }
+    };
+    bool sw_assigned = false;
+    for (int I = 0; I < ns; ++I) {
+        std::vector<int> bi;
+        for (int b = I * 4; b < std::min(nbx, I * 4 + 4); ++b) bi.push_back(b);
+        // diagonal super-tile (+ X'Y and Y'Y units when they fit in the same group)
+        {
+            std::vector<int> slots = bi;
+            std::vector<RawUnit> units;
+            for (size_t a = 0; a < bi.size(); ++a)
+                for (size_t b = a; b < bi.size(); ++b) {
+                    RawUnit u{bi[a], bi[b], a == b ? 2 : 1, a == b ? 1 : 0};
+                    if (a == b && !sw_assigned) {
+                        u.sums |= 2;
+                        sw_assigned = true;
+                    }
+                    units.push_back(u);
+                }
+            const bool merge_y = (int)bi.size() + nby <= MAXSLOT &&
+                                 (int)units.size() + (int)bi.size() * nby + (I == 0 ? nby : 0) <= NCW;
+            if (merge_y) {
+                for (int y = 0; y < nby; ++y) slots.push_back(nbx + y);
+                for (int b : bi)
+                    for (int y = 0; y < nby; ++y) units.push_back(RawUnit{b, nbx + y, 1, 0});
+                if (I == 0)
+                    for (int y = 0; y < nby; ++y) units.push_back(RawUnit{nbx + y, nbx + y, 2, 1});
+            }
+            emit(slots, units);
+            if (!merge_y) {
+                // separate X_I' Y groups, Y blocks taken 4 at a time
+                for (int y0 = 0; y0 < nby; y0 += 4) {
+                    std::vector<int> s2 = bi;
+                    std::vector<RawUnit> u2;
+                    for (int y = y0; y < std::min(nby, y0 + 4); ++y) s2.push_back(nbx + y);
+                    for (int b : bi)
+                        for (int y = y0; y < std::min(nby, y0 + 4); ++y)
+                            u2.push_back(RawUnit{b, nbx + y, 1, 0});
+                    emit(s2, u2);
+                }
+                if (I == 0) {
+                    for (int y0 = 0; y0 < nby; y0 += MAXSLOT) {
+                        std::vector<int> s3;
+                        std::vector<RawUnit> u3;
+                        for (int y = y0; y < std::min(nby, y0 + MAXSLOT); ++y) {
+                            s3.push_back(nbx + y);
+                            u3.push_back(RawUnit{nbx + y, nbx + y, 2, 1});
+                        }
+                        emit(s3, u3);
+                    }
+                }
+            }
+        }
+        for (int J = I + 1; J < ns; ++J) {
+            std::vector<int> slots = bi;
+            std::vector<int> bj;
+            for (int b = J * 4; b < std::min(nbx, J * 4 + 4); ++b) {
+                bj.push_back(b);
+                slots.push_back(b);
+            }
+            std::vector<RawUnit> units;
+            for (int a : bi)
+                for (int b : bj) units.push_back(RawUnit{a, b, 1, 0});
+            emit(slots, units);
+        }
+    }
+}
+
+static void build_segments(int64_t nstages, int ncta, Schedule& S) {
+    const int ng = (int)S.groups.size();
+    double total = 0;
+    for (int g = 0; g < ng; ++g) total += S.gcost[g] * (double)nstages;
+    const double share = total / ncta;
+    S.segs.clear();
+    S.cta_seg.assign(ncta + 1, 0);
+    S.group_seg.assign(ng + 1, 0);
+    // walk groups in order; CTA c owns the flattened cost interval [c*share, (c+1)*share)
+    std::vector<std::vector<SegDesc>> per_cta(ncta);
+    double pos = 0;  // flattened cost position of the start of the current group
+    for (int g = 0; g < ng; ++g) {
+        const double gc = S.gcost[g];
+        const double end = pos + gc * (double)nstages;
+        auto stage_at = [&](int cta) {  // first stage of this group owned by CTA `cta`
+            double b = ((double)cta * share - pos) / gc;
+            int64_t sb = (int64_t)(b + 0.5);
+            return std::max<int64_t>(0, std::min<int64_t>(nstages, sb));
+        };
+        int c_lo = std::min(ncta - 1, (int)(pos / share + 1e-9));
+        int c_hi = std::min(ncta - 1, (int)(end / share - 1e-9));
+        for (int cta = c_lo; cta <= c_hi; ++cta) {
+            const int64_t s = (cta == c_lo) ? 0 : stage_at(cta);
+            const int64_t e = (cta == c_hi) ? nstages : stage_at(cta + 1);
+            if (e > s) per_cta[cta].push_back(SegDesc{g, (int32_t)s, (int32_t)e, 0});
+        }
+        pos = end;
+    }
+    // segment order must be group-major for K1b (contiguous per group) and CTA-contiguous for K1:
+    // the walk above already emits both orders at once (CTAs take consecutive pieces).
+    for (int c = 0; c < ncta; ++c) {
+        S.cta_seg[c] = (int32_t)S.segs.size();
+        for (const SegDesc& sd : per_cta[c]) S.segs.push_back(sd);
+    }
+    S.cta_seg[ncta] = (int32_t)S.segs.size();
+    int cur = 0;
+    for (int g = 0; g < ng; ++g) {
+        S.group_seg[g] = cur;
+        while (cur < (int)S.segs.size() && S.segs[cur].group == g) ++cur;
+    }
+    S.group_seg[ng] = cur;
+}
+
+int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
+                 int64_t p, int64_t q, double* d_pivot) {
+    const int warps = 8;
+    const int grid = (int)((p + q + warps - 1) / warps);
+    pivot_kernel<<<grid, warps * 32, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
+                const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
+                double* d_packed, int accumulate) {
+    if (((uintptr_t)dX & 15) || ((uintptr_t)dY & 15) || (dw && ((uintptr_t)dw & 15)) || (ldx & 1) ||
+        (ldy & 1)) {
+        set_error("gram: device pointers must be 16-byte aligned and leading dimensions even "
+                  "(TMA requirement); repack the shard");
+        return JCB200_EALIGN;
+    }
+    const int64_t nstages = (n + KT - 1) / KT;
+    const int ncta = c->num_sms;
+    const int nbx = (int)((p + CB - 1) / CB);
+    // ---- schedule (cached on (p, q, nstages))
+    if (c->sk_p != p || c->sk_q != q || c->sk_nst != nstages) {
+        Schedule S;
+        build_groups(p, q, S);
+        build_segments(nstages, ncta, S);
+        const size_t gb = S.groups.size() * sizeof(GroupDesc), sb = S.segs.size() * sizeof(SegDesc),
+                     cb = S.cta_seg.size() * 4, qb = S.group_seg.size() * 4;
+        const size_t tot = gb + sb + cb + qb;
+        if (c->sched_host_bytes < tot) {
+            if (c->sched_host) cudaFreeHost(c->sched_host);
+            JCB_CUDA(cudaMallocHost(&c->sched_host, tot));
+            c->sched_host_bytes = tot;
+        }
+        JCB_TRY(ensure(c->sched_dev, tot));
+        // a previous launch may still read the old schedule: drain the stream before overwriting
+        JCB_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned char* h = (unsigned char*)c->sched_host;
+        memcpy(h, S.groups.data(), gb);
+        memcpy(h + gb, S.segs.data(), sb);
+        memcpy(h + gb + sb, S.cta_seg.data(), cb);
+        memcpy(h + gb + sb + cb, S.group_seg.data(), qb);
+        JCB_CUDA(cudaMemcpyAsync(c->sched_dev.p, h, tot, cudaMemcpyHostToDevice, c->stream));
+        c->sk_p = p;
+        c->sk_q = q;
+        c->sk_nst = nstages;
+        c->sk_ngroups = (int)S.groups.size();
+        c->sk_nsegs = (int)S.segs.size();
+    }
+    const int ng = c->sk_ngroups, nsegs = c->sk_nsegs;
+    unsigned char* d = (unsigned char*)c->sched_dev.p;
+    const GroupDesc* dgroups = (const GroupDesc*)d;
+    const SegDesc* dsegs = (const SegDesc*)(d + (size_t)ng * sizeof(GroupDesc));
+    const int32_t* dcta = (const int32_t*)(d + (size_t)ng * sizeof(GroupDesc) +
+                                           (size_t)nsegs * sizeof(SegDesc));
+    const int32_t* dgseg = dcta + (ncta + 1);
+    JCB_TRY(ensure(c->partials, (size_t)nsegs * NCW * UNIT_STRIDE * 8));
+
+    CUtensorMap mapX, mapY, mapW;
+    JCB_TRY(make_map_2d(&mapX, dX, n, p, ldx, KT, CB));
+    JCB_TRY(make_map_2d(&mapY, dY, n, q, ldy, KT, CB));
+    if (dw) {
+        JCB_TRY(make_map_1d(&mapW, dw, n, KT));
+    } else {
+        mapW = mapX;
+    }
+    GramParams prm;
+    prm.groups = dgroups;
+    prm.segs = dsegs;
+    prm.cta_seg = dcta;
+    prm.pivot = d_pivot;
+    prm.partials = (double*)c->partials.p;
+    prm.n = n;
+    prm.p = (int)p;
+    prm.q = (int)q;
+    prm.nbx = nbx;
+    prm.weighted = dw ? 1 : 0;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        JCB_CUDA(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K1_SMEM));
+        JCB_CUDA(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K1_SMEM));
+        attr_set = true;
+    }
+    phase_begin(c, JCB200_T_GRAM);
+    if (dw)
+        gram_kernel<true><<<ncta, K1_THREADS, K1_SMEM, c->stream>>>(mapX, mapY, mapW, prm);
+    else
+        gram_kernel<false><<<ncta, K1_THREADS, K1_SMEM, c->stream>>>(mapX, mapY, mapW, prm);
+    JCB_LAUNCH_CHECK();
+    phase_end(c, JCB200_T_GRAM);
+    phase_begin(c, JCB200_T_REDUCE);
+    gram_reduce_kernel<<<ng * NCW, 256, 0, c->stream>>>(dgroups, dgseg, (const double*)c->partials.p,
+                                                        d_packed, (int)p, (int)q, nbx, accumulate);
+    JCB_LAUNCH_CHECK();
+    phase_end(c, JCB200_T_REDUCE);
+    return 0;
+}
+
+}  // namespace jcb

@@ -1,0 +1,389 @@
+// K3 (finalise the all-reduced Gram) and K4 (persistent latent-variable loop).
+//
+// K3 replaces colmean / colstd / center! / cscale! (/root/reference/src/plskern.jl:118-129,
+// utility.jl:195,264,314-323) in Gram form: with S = sum(w), delta = s/S (s = weighted column sums
+// about the pivot c):  means = c + delta,  Xc'DXc = G/S - delta delta',  scales = sqrt(diag) when
+// scal, and the scaled cross-products D^-1 (.) D^-1.  The upper triangle is mirrored.
+//
+// K4 replaces the LV loop (/root/reference/src/plskern.jl:149-175).  Gram-form recurrences:
+//   w  = XtY[:,1]/||.||                      (q == 1, :151-152)
+//      = XtY v / ||XtY v||, v = dominant eigenvector of XtY'XtY  (q > 1; equals svd(XtY).U[:,1] up
+//        to sign, :154)
+//   r  = w - sum_{j<a} (w'P_j) R_j           (:156-161, classical Gram-Schmidt on the original w)
+//   zp = XtX r ; tt = r'zp                   (:162-164,167 without touching X)
+//   c  = XtY' r / tt                          (:165-166, XtY before deflation)
+//   XtY -= zp c' ; P_a = zp/tt                (:168-169)
+// One cluster of 8 CTAs runs the whole loop: the p x p matvec and the deflation are row-sliced across
+// the CTAs (two cluster barriers per LV), everything O(p q) is recomputed redundantly — and
+// bit-identically — by every CTA so no broadcast is needed.
+#include <cooperative_groups.h>
+
+#include "jcb_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace jcb {
+
+constexpr int LV_THREADS = 512;
+constexpr int LV_CLUSTER = 8;
+
+// ----------------------------------------------------------------------------------------- K3
+// stats: delta, means, scales (one block)
+__global__ void finalize_stats_kernel(const double* __restrict__ packed,
+                                      const double* __restrict__ pivot, int p, int q, int scal,
+                                      double* __restrict__ xmeans, double* __restrict__ xscales,
+                                      double* __restrict__ ymeans, double* __restrict__ yscales,
+                                      double* __restrict__ sumw, double* __restrict__ delta) {
+    const int64_t P = p, Q = q;
+    const double* gxx = packed;
+    const double* gyy = packed + P * P + P * Q;
+    const double* sx = gyy + Q;
+    const double* sy = sx + P;
+    const double S = sy[Q];
+    if (threadIdx.x == 0 && blockIdx.x == 0) *sumw = S;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p + q; j += gridDim.x * blockDim.x) {
+        if (j < p) {
+            const double d = sx[j] / S;
+            delta[j] = d;
+            xmeans[j] = pivot[j] + d;
+            xscales[j] = scal ? sqrt(gxx[j + (int64_t)j * P] / S - d * d) : 1.0;
+        } else {
+            const int k = j - p;
+            const double d = sy[k] / S;
+            delta[j] = d;
+            ymeans[k] = pivot[j] + d;
+            yscales[k] = scal ? sqrt(gyy[k] / S - d * d) : 1.0;
+        }
+    }
+}
+
+// XtX (full, mirrored) and XtY, centred exactly and scaled
+__global__ void finalize_gram_kernel(const double* __restrict__ packed,
+                                     const double* __restrict__ delta,
+                                     const double* __restrict__ xscales,
+                                     const double* __restrict__ yscales, int p, int q,
+                                     double* __restrict__ XtX, double* __restrict__ XtY) {
+    const int64_t P = p, Q = q;
+    const double S = packed[P * P + P * Q + Q + P + Q];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // row
+    const int j = blockIdx.y;                              // column of [XtX | XtY]
+    if (i >= p) return;
+    if (j < p) {
+        if (i > j) return;
+        const double v = (packed[i + (int64_t)j * P] / S - delta[i] * delta[j]) /
+                         (xscales[i] * xscales[j]);
+        XtX[i + (int64_t)j * P] = v;
+        XtX[j + (int64_t)i * P] = v;
+    } else {
+        const int k = j - p;
+        XtY[i + (int64_t)k * P] =
+            (packed[P * P + i + (int64_t)k * P] / S - delta[i] * delta[p + k]) /
+            (xscales[i] * yscales[k]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------- K4
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum; every thread receives the result. `red` holds >= 32 doubles.
+__device__ double block_sum(double v, double* red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = (lane < (LV_THREADS >> 5)) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+struct LvParams {
+    const double* XtX;   // p x p, symmetric, read only
+    double* XtY;         // p x q, deflated in place
+    double* zp;          // p, exchange buffer
+    double* P;
+    double* R;
+    double* W;
+    double* C;
+    double* TT;
+    int p, q, nlv;
+};
+
+__global__ void __cluster_dims__(LV_CLUSTER, 1, 1) __launch_bounds__(LV_THREADS, 1)
+lvloop_kernel(const LvParams prm) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double sm[];
+    const int p = prm.p, q = prm.q, nlv = prm.nlv;
+    double* w_s = sm;             // p
+    double* r_s = w_s + p;        // p
+    double* zp_s = r_s + p;       // p
+    double* A_s = zp_s + p;       // q*q
+    double* B_s = A_s + q * q;    // q*q
+    double* M_s = B_s + q * q;    // q*q
+    double* v_s = M_s + q * q;    // q
+    double* c_s = v_s + q;        // q
+    double* d_s = c_s + q;        // nlv (dots w'P_j)
+    double* red = d_s + nlv;      // 64
+    __shared__ int flag_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = LV_THREADS >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int per = (p + LV_CLUSTER - 1) / LV_CLUSTER;
+    const int lo = min(p, rank * per), hi = min(p, lo + per);
+    const int64_t P64 = p;
+
+    for (int a = 0; a < nlv; ++a) {
+        // ---------------------------------------------------------------- (1) weight vector w
+        if (q == 1) {
+            double s = 0.0;
+            for (int k = tid; k < p; k += LV_THREADS) {
+                const double x = __ldcg(prm.XtY + k);
+                w_s[k] = x;
+                s += x * x;
+            }
+            const double nrm = sqrt(block_sum(s, red));
+            for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+        } else {
+            // M = XtY' XtY (symmetric q x q): one warp per (i <= j) pair
+            const int npair = q * (q + 1) / 2;
+            for (int pr = warp; pr < npair; pr += nwarp) {
+                int i = 0, rem = pr;
+                while (rem >= q - i) { rem -= q - i; ++i; }
+                const int j = i + rem;
+                const double* ci = prm.XtY + (int64_t)i * P64;
+                const double* cj = prm.XtY + (int64_t)j * P64;
+                double s = 0.0;
+                for (int k = lane; k < p; k += 32) s += __ldcg(ci + k) * __ldcg(cj + k);
+                s = warp_sum(s);
+                if (lane == 0) { M_s[i * q + j] = s; M_s[j * q + i] = s; }
+            }
+            __syncthreads();
+            // dominant eigenvector by repeated squaring of the trace-normalised matrix
+            double tr = 0.0;
+            for (int i = 0; i < q; ++i) tr += M_s[i * q + i];
+            for (int e = tid; e < q * q; e += LV_THREADS) A_s[e] = M_s[e] / tr;
+            __syncthreads();
+            for (int iter = 0; iter < 64; ++iter) {
+                for (int e = tid; e < q * q; e += LV_THREADS) {
+                    const int i = e / q, j = e - i * q;
+                    double s = 0.0;
+                    for (int k = 0; k < q; ++k) s += A_s[i * q + k] * A_s[k * q + j];
+                    B_s[e] = s;
+                }
+                if (tid == 0) flag_s = 0;
+                __syncthreads();
+                double t2 = 0.0;
+                for (int i = 0; i < q; ++i) t2 += B_s[i * q + i];
+                bool moved = false;
+                for (int e = tid; e < q * q; e += LV_THREADS) {
+                    const double nv = B_s[e] / t2;
+                    if (fabs(nv - A_s[e]) > 1e-15) moved = true;
+                    A_s[e] = nv;
+                }
+                if (moved) flag_s = 1;
+                __syncthreads();
+                const int f = flag_s;
+                __syncthreads();
+                if (!f) break;
+            }
+            // v = column with the largest diagonal entry, then two refining power steps on M
+            if (warp == 0) {
+                int best = 0;
+                for (int i = 1; i < q; ++i) if (A_s[i * q + i] > A_s[best * q + best]) best = i;
+                for (int i = lane; i < q; i += 32) v_s[i] = A_s[i * q + best];
+                __syncwarp();
+                for (int rep = 0; rep < 3; ++rep) {
+                    double s = 0.0;
+                    for (int i = lane; i < q; i += 32) s += v_s[i] * v_s[i];
+                    s = sqrt(warp_sum(s));
+                    __syncwarp();
+                    for (int i = lane; i < q; i += 32) v_s[i] /= s;
+                    __syncwarp();
+                    if (rep == 2) break;
+                    for (int i = lane; i < q; i += 32) {
+                        double t = 0.0;
+                        for (int k = 0; k < q; ++k) t += M_s[i * q + k] * v_s[k];
+                        c_s[i] = t;
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < q; i += 32) v_s[i] = c_s[i];
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // w = XtY v / ||.||
+            double s = 0.0;
+            for (int k = tid; k < p; k += LV_THREADS) {
+                double t = 0.0;
+                for (int j = 0; j < q; ++j) t += __ldcg(prm.XtY + k + (int64_t)j * P64) * v_s[j];
+                w_s[k] = t;
+                s += t * t;
+            }
+            const double nrm = sqrt(block_sum(s, red));
+            for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- (2) r
+        for (int j = warp; j < a; j += nwarp) {
+            const double* pj = prm.P + (int64_t)j * P64;
+            double s = 0.0;
+            for (int k = lane; k < p; k += 32) s += w_s[k] * __ldcg(pj + k);
+            s = warp_sum(s);
+            if (lane == 0) d_s[j] = s;
+        }
+        __syncthreads();
+        for (int k = tid; k < p; k += LV_THREADS) {
+            double rv = w_s[k];
+            for (int j = 0; j < a; ++j) rv -= d_s[j] * __ldcg(prm.R + k + (int64_t)j * P64);
+            r_s[k] = rv;
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- (3) zp slice = XtX[lo:hi, :] r
+        for (int i = lo + warp; i < hi; i += nwarp) {
+            const double* row = prm.XtX + (int64_t)i * P64;   // symmetric: row i == column i
+            double s0 = 0.0, s1 = 0.0;
+            int k = lane;
+            for (; k + 32 < p; k += 64) {
+                s0 += row[k] * r_s[k];
+                s1 += row[k + 32] * r_s[k + 32];
+            }
+            if (k < p) s0 += row[k] * r_s[k];
+            const double s = warp_sum(s0 + s1);
+            if (lane == 0) __stcg(prm.zp + i, s);
+        }
+        // u = XtY' r (pre-deflation XtY; c = u / tt once tt is known)
+        for (int j = warp; j < q; j += nwarp) {
+            const double* cj = prm.XtY + (int64_t)j * P64;
+            double t = 0.0;
+            for (int k = lane; k < p; k += 32) t += __ldcg(cj + k) * r_s[k];
+            t = warp_sum(t);
+            if (lane == 0) c_s[j] = t;
+        }
+        // barrier 1: zp slices visible; every CTA has finished reading the pre-deflation XtY
+        cluster.sync();
+        // ---------------------------------------------------------------- (4) tt, c
+        double s = 0.0;
+        for (int k = tid; k < p; k += LV_THREADS) {
+            const double z = __ldcg(prm.zp + k);
+            zp_s[k] = z;
+            s += r_s[k] * z;
+        }
+        const double tt = block_sum(s, red);
+        __syncthreads();
+        for (int j = tid; j < q; j += LV_THREADS) c_s[j] /= tt;
+        __syncthreads();
+        // ---------------------------------------------------------------- (5) deflate own slice, store
+        const int nsl = hi - lo;
+        for (int e = tid; e < nsl * q; e += LV_THREADS) {
+            const int j = e / nsl, i = lo + (e - j * nsl);
+            double* dst = prm.XtY + i + (int64_t)j * P64;
+            __stcg(dst, __ldcg(dst) - zp_s[i] * c_s[j]);
+        }
+        for (int i = lo + tid; i < hi; i += LV_THREADS) {
+            __stcg(prm.P + i + (int64_t)a * P64, zp_s[i] / tt);
+            __stcg(prm.R + i + (int64_t)a * P64, r_s[i]);
+            prm.W[i + (int64_t)a * P64] = w_s[i];
+        }
+        if (rank == 0) {
+            for (int j = tid; j < q; j += LV_THREADS) prm.C[j + (int64_t)a * q] = c_s[j];
+            if (tid == 0) prm.TT[a] = tt;
+        }
+        // barrier 2: deflated XtY and columns a of P, R visible to the whole cluster
+        cluster.sync();
+    }
+}
+
+int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
+                 int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
+                 double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
+                 double* dsumw) {
+    // workspace: XtX p*p | XtY p*q | delta p+q | zp p
+    const size_t need = (size_t)(p * p + p * q + (p + q) + p) * 8;
+    JCB_TRY(ensure(c->solve_ws, need));
+    double* XtX = (double*)c->solve_ws.p;
+    double* XtY = XtX + p * p;
+    double* delta = XtY + p * q;
+    double* zp = delta + (p + q);
+
+    phase_begin(c, JCB200_T_FINALIZE);
+    finalize_stats_kernel<<<(int)((p + q + 255) / 256), 256, 0, c->stream>>>(
+        d_packed, d_pivot, (int)p, (int)q, scal, dxmeans, dxscales, dymeans, dyscales, dsumw, delta);
+    JCB_LAUNCH_CHECK();
+    dim3 grid((unsigned)((p + 127) / 128), (unsigned)(p + q));
+    finalize_gram_kernel<<<grid, 128, 0, c->stream>>>(d_packed, delta, dxscales, dyscales, (int)p,
+                                                      (int)q, XtX, XtY);
+    JCB_LAUNCH_CHECK();
+    phase_end(c, JCB200_T_FINALIZE);
+
+    if (nlv <= 0) return 0;
+    LvParams prm;
+    prm.XtX = XtX;
+    prm.XtY = XtY;
+    prm.zp = zp;
+    prm.P = dP;
+    prm.R = dR;
+    prm.W = dW;
+    prm.C = dC;
+    prm.TT = dTT;
+    prm.p = (int)p;
+    prm.q = (int)q;
+    prm.nlv = nlv;
+    const size_t smem = (size_t)(3 * p + 3 * q * q + 2 * q + nlv + 64) * 8;
+    if (smem > 200 * 1024) {
+        set_error("solve: p=%lld q=%lld need %zu bytes of shared memory (> 200 KB)", (long long)p,
+                  (long long)q, smem);
+        return JCB200_EINVAL;
+    }
+    JCB_CUDA(cudaFuncSetAttribute(lvloop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    phase_begin(c, JCB200_T_LVLOOP);
+    lvloop_kernel<<<LV_CLUSTER, LV_THREADS, smem, c->stream>>>(prm);
+    JCB_LAUNCH_CHECK();
+    phase_end(c, JCB200_T_LVLOOP);
+    return 0;
+}
+
+// coef (plskern.jl:207-217): B = D(1/xs) R[:,1:k] C[:,1:k]' D(ys); int = ymeans' - xmeans' B.
+__global__ void coef_B_kernel(const double* __restrict__ R, const double* __restrict__ C,
+                              const double* __restrict__ xs, const double* __restrict__ ys, int p,
+                              int q, int k, double* __restrict__ B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= p) return;
+    double s = 0.0;
+    for (int a = 0; a < k; ++a) s += R[i + (int64_t)a * p] * C[j + (int64_t)a * q];
+    B[i + (int64_t)j * p] = (1.0 / xs[i]) * s * ys[j];
+}
+__global__ void coef_int_kernel(const double* __restrict__ B, const double* __restrict__ xmeans,
+                                const double* __restrict__ ymeans, int p, int q,
+                                double* __restrict__ intercept) {
+    const int j = blockIdx.x;
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) s += xmeans[i] * B[i + (int64_t)j * p];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) intercept[j] = ymeans[j] - t;
+    }
+}
+
+int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmeans,
+                const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
+                int64_t q, int k, double* dB, double* dint) {
+    dim3 grid((unsigned)((p + 127) / 128), (unsigned)q);
+    coef_B_kernel<<<grid, 128, 0, c->stream>>>(dR, dC, dxscales, dyscales, (int)p, (int)q, k, dB);
+    JCB_LAUNCH_CHECK();
+    coef_int_kernel<<<(unsigned)q, 256, 0, c->stream>>>(dB, dxmeans, dymeans, (int)p, (int)q, dint);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace jcb

@@ -1,0 +1,355 @@
+// K5 / K6 — streaming FP64 tensor-core GEMM over the rows of X:
+//     Out = bias' + ((X - mu) ./ sigma) * M           (M is p x ncol, ncol small)
+// K5: scores T = Xc R (fit, /root/reference/src/plskern.jl:162,170) and transform (:187-195);
+//     single-k predictions with M = B_k, bias = ymeans (:233-234).
+// K6: predict for a whole contiguous range k_lo:k_hi (:226-238) in ONE pass over X: the tile of
+//     scores T = Xc R is formed once and pred_k = ymeans + sum_{j<k} t_j (c_j .* yscales)' is
+//     accumulated over k in the epilogue, writing one m x q matrix per k.
+//
+// Design: X is column-major, so a tile of 128 rows x 32 columns is 32 contiguous 1 KB column
+// segments; the producer warp brings each with one bulk async copy (cp.async.bulk, completes on an
+// mbarrier) into a [column][132]-pitched shared tile — the 132 pitch makes the A-fragment loads
+// (128-bit, two rows per lane) conflict free.  M is pre-packed (1/sigma folded in, zero padded) in the
+// exact staged layout, one bulk copy per stage.  8 consumer warps own 16 rows each; centring happens
+// on the fragments.  Results are staged through shared memory so global stores are 128-byte rows.
+#include <algorithm>
+#include <cstring>
+
+#include "jcb_internal.cuh"
+
+namespace jcb {
+
+constexpr int XM_MT = 128;        // rows per tile
+constexpr int XM_PITCH = 132;     // shared pitch of a column (doubles)
+constexpr int XM_KC = 32;         // columns of X per stage
+constexpr int XM_MPITCH = 36;     // shared pitch of a row of packed M^T (doubles)
+constexpr int XM_NCW = 8;         // consumer warps
+constexpr int XM_THREADS = (XM_NCW + 1) * 32;
+constexpr int XM_MAXNB = 8;       // up to 64 output columns per pass
+
+struct XmulParams {
+    const double* X;
+    int64_t ldx;
+    int64_t m;
+    int p;
+    int nchunk;            // ceil(p / 32)
+    const double* Mt;      // packed: [chunk][NP][36]
+    const double* mu;      // padded to nchunk*32
+    const double* zeros;   // >= 128 zero doubles (source for padding columns)
+    const double* bias;    // NP (zero padded) or nullptr
+    double* Out;
+    int64_t ldo;
+    int ncol;              // real output columns in this pass
+    int aligned;           // X is 16-byte aligned with even ldx: bulk copies allowed
+    // sweep epilogue
+    const double* Cy;      // [a][q]: C[j,k] * yscales[j]
+    const double* ymeans;
+    double* Pred;          // (k_hi-k_lo+1) matrices m x q
+    int q, k_lo, k_hi;
+    int nstage;
+};
+
+// packs M (p x ncol, ld ldm) into Mt[chunk][n][36] with 1/sigma folded in; pads mu
+__global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, const double* __restrict__ sigma,
+                                 const double* __restrict__ mu, int p, int ncol, int NP, int nchunk,
+                                 double* __restrict__ Mt, double* __restrict__ mu_pad) {
+    const int64_t total = (int64_t)nchunk * NP * XM_MPITCH;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % XM_MPITCH);
+        const int n = (int)((e / XM_MPITCH) % NP);
+        const int ch = (int)(e / ((int64_t)XM_MPITCH * NP));
+        const int k = ch * XM_KC + kk;
+        double v = 0.0;
+        if (kk < XM_KC && k < p && n < ncol) v = M[k + (int64_t)n * ldm] / (sigma ? sigma[k] : 1.0);
+        Mt[e] = v;
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nchunk * XM_KC; k += gridDim.x * blockDim.x)
+        mu_pad[k] = k < p ? mu[k] : 0.0;
+}
+
+template <int NPB, bool SWEEP>
+__global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams prm) {
+    constexpr int NP = NPB * 8;
+    constexpr int XBYTES = XM_KC * XM_PITCH * 8;        // 33792
+    constexpr int MBYTES = NP * XM_MPITCH * 8;
+    constexpr int STAGE = XBYTES + MBYTES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int nstage = prm.nstage;
+    unsigned char* stage_base = smem;
+    double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NP][132]
+    double* mu_s = out_s + NP * XM_PITCH;                                        // nchunk*32
+    uint64_t* full = reinterpret_cast<uint64_t*>(mu_s + prm.nchunk * XM_KC);
+    uint64_t* empty = full + nstage;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < prm.nchunk * XM_KC; k += XM_THREADS) mu_s[k] = prm.mu[k];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], XM_NCW);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
+    const int nchunk = prm.nchunk;
+    uint32_t it = 0;
+
+    if (warp == XM_NCW) {
+        // ------------------------------------------------------------------ producer warp
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int64_t row0 = t * XM_MT;
+            const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
+            const bool bulk = prm.aligned && rows == XM_MT;
+            for (int ch = 0; ch < nchunk; ++ch, ++it) {
+                const int buf = it % nstage;
+                const uint32_t ph = (it / nstage) & 1;
+                if (lane == 0) mbar_wait(&empty[buf], ph ^ 1);
+                __syncwarp();
+                double* xs = reinterpret_cast<double*>(stage_base + (size_t)buf * STAGE);
+                double* ms = xs + XM_KC * XM_PITCH;
+                const double* msrc = prm.Mt + (int64_t)ch * NP * XM_MPITCH;
+                if (bulk) {
+                    if (lane == 0) mbar_arrive_expect_tx(&full[buf], XM_KC * XM_MT * 8 + MBYTES);
+                    __syncwarp();
+                    const int k = ch * XM_KC + lane;
+                    const double* src = k < prm.p ? prm.X + row0 + (int64_t)k * prm.ldx : prm.zeros;
+                    bulk_load(xs + lane * XM_PITCH, src, XM_MT * 8, &full[buf]);
+                    if (lane == 0) bulk_load(ms, msrc, MBYTES, &full[buf]);
+                } else {
+                    // ragged / unaligned tile: plain loads through registers
+                    for (int kc = 0; kc < XM_KC; ++kc) {
+                        const int k = ch * XM_KC + kc;
+                        for (int r = lane; r < XM_MT; r += 32)
+                            xs[kc * XM_PITCH + r] =
+                                (k < prm.p && r < rows) ? prm.X[row0 + r + (int64_t)k * prm.ldx] : 0.0;
+                    }
+                    for (int e = lane; e < NP * XM_MPITCH; e += 32) ms[e] = msrc[e];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[buf]);   // release: generic-proxy writes above
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int g = lane >> 2, kk = lane & 3;
+    const int m0 = warp * 16;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * XM_MT;
+        const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
+        double acc[2][NPB][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nb = 0; nb < NPB; ++nb) acc[h][nb][0] = acc[h][nb][1] = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch, ++it) {
+            const int buf = it % nstage;
+            const uint32_t ph = (it / nstage) & 1;
+            mbar_wait(&full[buf], ph);
+            const double* xs = reinterpret_cast<const double*>(stage_base + (size_t)buf * STAGE);
+            const double* ms = xs + XM_KC * XM_PITCH;
+            const double* mus = mu_s + ch * XM_KC;
+#pragma unroll
+            for (int k4 = 0; k4 < XM_KC / 4; ++k4) {
+                const int k = k4 * 4 + kk;
+                double2 a = *reinterpret_cast<const double2*>(xs + k * XM_PITCH + m0 + 2 * g);
+                const double mk = mus[k];
+                a.x -= mk;
+                a.y -= mk;
+#pragma unroll
+                for (int nb = 0; nb < NPB; ++nb) {
+                    const double b = ms[(nb * 8 + g) * XM_MPITCH + k];
+                    dmma(acc[0][nb][0], acc[0][nb][1], a.x, b);
+                    dmma(acc[1][nb][0], acc[1][nb][1], a.y, b);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[buf]);
+        }
+        // ---- epilogue: fragments -> shared (this warp's 16 rows) -> 128-byte global rows
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nb = 0; nb < NPB; ++nb) {
+                out_s[(nb * 8 + 2 * kk) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][0];
+                out_s[(nb * 8 + 2 * kk + 1) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][1];
+            }
+        __syncwarp();
+        const int r = lane & 15, half = lane >> 4;
+        const bool rok = (m0 + r) < rows;
+        if (!SWEEP) {
+            for (int col = half; col < prm.ncol; col += 2) {
+                if (rok) {
+                    double v = out_s[col * XM_PITCH + m0 + r];
+                    if (prm.bias) v += prm.bias[col];
+                    prm.Out[row0 + m0 + r + (int64_t)col * prm.ldo] = v;
+                }
+            }
+        } else {
+            // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]
+            const int q = prm.q;
+            const int64_t msz = prm.m * (int64_t)q;
+            for (int j = half; j < q; j += 2) {
+                double pv = prm.ymeans[j];
+                for (int k = 0; k <= prm.k_hi; ++k) {
+                    if (k >= prm.k_lo && rok)
+                        prm.Pred[(int64_t)(k - prm.k_lo) * msz + row0 + m0 + r + (int64_t)j * prm.m] = pv;
+                    if (k < prm.k_hi) pv += out_s[k * XM_PITCH + m0 + r] * prm.Cy[k * q + j];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Cy[k][j] = C[j,k] * yscales[j]
+__global__ void sweep_cy_kernel(const double* __restrict__ C, const double* __restrict__ ys, int q, int a,
+                                double* __restrict__ Cy) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a * q) return;
+    const int k = e / q, j = e - k * q;
+    Cy[e] = C[j + (int64_t)k * q] * ys[j];
+}
+
+template <int NPB, bool SWEEP>
+static int launch_xmul_t(Ctx* c, XmulParams& prm) {
+    constexpr int NP = NPB * 8;
+    const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
+    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128;
+    int nstage = (int)((220 * 1024 - fixed) / stage);
+    if (nstage > 4) nstage = 4;
+    if (nstage < 2) {
+        set_error("xmul: p=%d too large for the shared-memory budget", prm.p);
+        return JCB200_EINVAL;
+    }
+    prm.nstage = nstage;
+    const int smem = nstage * stage + fixed;
+    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  smem));
+    const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
+    const int grid = (int)std::min<int64_t>(ntiles, c->num_sms);
+    xmul_kernel<NPB, SWEEP><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <bool SWEEP>
+static int dispatch_xmul(Ctx* c, XmulParams& prm, int npb) {
+    switch (npb) {
+        case 1: return launch_xmul_t<1, SWEEP>(c, prm);
+        case 2: return launch_xmul_t<2, SWEEP>(c, prm);
+        case 3: return launch_xmul_t<3, SWEEP>(c, prm);
+        case 4: return launch_xmul_t<4, SWEEP>(c, prm);
+        case 5: return launch_xmul_t<5, SWEEP>(c, prm);
+        case 6: return launch_xmul_t<6, SWEEP>(c, prm);
+        case 7: return launch_xmul_t<7, SWEEP>(c, prm);
+        default: return launch_xmul_t<8, SWEEP>(c, prm);
+    }
+}
+
+// workspace layout: zeros[128] | mu_pad | bias_pad[64] | Cy | Mt
+static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
+                       const double* dsigma, const double* dM, int64_t ldm, int ncol_total,
+                       const double* dbias, double* dOut, int64_t ldo, bool sweep, const double* dC,
+                       const double* dys, const double* dymeans, int q, int k_lo, int k_hi,
+                       double* dPred) {
+    const int nchunk = (int)((p + XM_KC - 1) / XM_KC);
+    const int maxcol = XM_MAXNB * 8;
+    if (sweep && ncol_total > maxcol) {
+        set_error("predict sweep supports at most %d latent variables in one pass", maxcol);
+        return JCB200_EINVAL;
+    }
+    const size_t ws_doubles = 128 + (size_t)nchunk * XM_KC + 64 + (size_t)maxcol * (q > 0 ? q : 1) +
+                              (size_t)nchunk * maxcol * XM_MPITCH;
+    JCB_TRY(ensure(c->xmul_ws, ws_doubles * 8));
+    double* zeros = (double*)c->xmul_ws.p;
+    double* mu_pad = zeros + 128;
+    double* bias_pad = mu_pad + (size_t)nchunk * XM_KC;
+    double* Cy = bias_pad + 64;
+    double* Mt = Cy + (size_t)maxcol * (q > 0 ? q : 1);
+    JCB_CUDA(cudaMemsetAsync(zeros, 0, 128 * 8, c->stream));
+    const int aligned = (((uintptr_t)dX & 15) == 0 && (ldx & 1) == 0) ? 1 : 0;
+
+    for (int c0 = 0; c0 < ncol_total; c0 += maxcol) {
+        const int ncol = std::min(maxcol, ncol_total - c0);
+        const int npb = (ncol + 7) / 8, NP = npb * 8;
+        xmul_pack_kernel<<<64, 256, 0, c->stream>>>(dM + (int64_t)c0 * ldm, ldm, dsigma, dmu, (int)p, ncol,
+                                                    NP, nchunk, Mt, mu_pad);
+        JCB_LAUNCH_CHECK();
+        XmulParams prm;
+        memset(&prm, 0, sizeof(prm));
+        prm.X = dX;
+        prm.ldx = ldx;
+        prm.m = m;
+        prm.p = (int)p;
+        prm.nchunk = nchunk;
+        prm.Mt = Mt;
+        prm.mu = mu_pad;
+        prm.zeros = zeros;
+        prm.bias = dbias ? dbias + c0 : nullptr;
+        prm.Out = dOut ? dOut + (int64_t)c0 * ldo : nullptr;
+        prm.ldo = ldo;
+        prm.ncol = ncol;
+        prm.aligned = aligned;
+        if (sweep) {
+            sweep_cy_kernel<<<(ncol * q + 255) / 256, 256, 0, c->stream>>>(dC, dys, q, ncol, Cy);
+            JCB_LAUNCH_CHECK();
+            prm.Cy = Cy;
+            prm.ymeans = dymeans;
+            prm.Pred = dPred;
+            prm.q = q;
+            prm.k_lo = k_lo;
+            prm.k_hi = k_hi;
+            JCB_TRY(dispatch_xmul<true>(c, prm, npb));
+        } else {
+            JCB_TRY(dispatch_xmul<false>(c, prm, npb));
+        }
+    }
+    return 0;
+}
+
+int launch_xmul(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
+                const double* dsigma, const double* dM, int64_t ldm, int ncol, const double* dbias,
+                double* dOut, int64_t ldo) {
+    if (ncol <= 0 || m <= 0) return 0;
+    phase_begin(c, JCB200_T_SCORES);
+    int r = xmul_common(c, dX, ldx, m, p, dmu, dsigma, dM, ldm, ncol, dbias, dOut, ldo, false, nullptr,
+                        nullptr, nullptr, 0, 0, 0, nullptr);
+    phase_end(c, JCB200_T_SCORES);
+    return r;
+}
+
+// pred_k for k < k_lo..k_hi all need only the first k_hi score columns
+__global__ void fill_ymeans_kernel(const double* __restrict__ ymeans, int64_t m, int q, int nk,
+                                   double* __restrict__ Pred) {
+    const int64_t total = (int64_t)nk * m * q;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x)
+        Pred[e] = ymeans[(e / m) % q];
+}
+
+int launch_predict_sweep(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,
+                         const double* dR, const double* dC, int a, const double* dxmeans,
+                         const double* dxscales, const double* dymeans, const double* dyscales,
+                         int k_lo, int k_hi, double* dPred) {
+    if (m <= 0) return 0;
+    phase_begin(c, JCB200_T_SCORES);
+    int r = 0;
+    if (k_hi == 0) {
+        // nlv = 0 only: predictions are ymeans broadcast (plskern.jl:210-215,234)
+        fill_ymeans_kernel<<<256, 256, 0, c->stream>>>(dymeans, m, (int)q, k_hi - k_lo + 1, dPred);
+        g_launches++;
+        if (cudaGetLastError() != cudaSuccess) r = 1;
+    } else {
+        r = xmul_common(c, dX, ldx, m, p, dxmeans, dxscales, dR, p, k_hi, nullptr, nullptr, 0, true, dC,
+                        dyscales, dymeans, (int)q, k_lo, k_hi, dPred);
+    }
+    phase_end(c, JCB200_T_SCORES);
+    return r;
+}
+
+}  // namespace jcb

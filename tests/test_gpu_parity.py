@@ -1,0 +1,157 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host-pointer entry points, the call a
+Julia `ccall` would make), against the NumPy oracle and the committed golden fixtures.
+
+Tolerance (north star): relative Frobenius error <= 1e-10 on B, T and predictions after per-LV sign
+alignment.  For the q = 1 `rand` case (C3) the reference cannot reproduce its own late
+LVs: columns where ||XtY_a|| / ||XtY_1|| < 1e-6 are graded on B / predictions only.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import make_golden, synth
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def jc():
+    import __graft_entry__ as ge
+    ge.build()
+    import jchemo_b200
+    return jchemo_b200
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_wscal", "c2_cut", "c3_cut", "c5_cut", "edge_odd"])
+def test_fit_matches_golden_and_oracle(jc, name):
+    cfg, z = load_golden(name)
+    X, Y, w, Xnew = make_golden.inputs(cfg)
+    X0, Y0 = X.copy(), Y.copy()
+    fm = jc.plskern(X, Y, None if cfg["uniform"] else w, nlv=cfg["nlv"], scal=cfg["scal"])
+    assert np.array_equal(X, X0) and np.array_equal(Y, Y0)          # plskern leaves inputs untouched
+    a = z["TT"].shape[0]
+    assert fm.T.shape == (cfg["n"], a) and fm.P.shape == (cfg["p"], a) and fm.C.shape == (cfg["q"], a)
+    assert fm.niter is None and fm.V is fm.P
+    for f in ["xmeans", "xscales", "ymeans", "yscales"]:
+        assert relerr(getattr(fm, f), z[f]) < 1e-13, f
+    assert relerr(fm.weights[z["rows"]], z["weights_rows"]) < 1e-14
+    s = np.sign(np.sum(z["W"] * fm.W, axis=0))
+    ok = np.ones(a, dtype=bool)
+    if cfg["q"] == 1:
+        # ||XtY_a|| = |c_a| * tt_a / |r_a' XtY_a / ||XtY_a||| ~ |C[0,a]| TT[a] up to O(1): conditioning proxy
+        k = np.abs(z["C"][0]) * z["TT"]
+        ok = k / k[0] > 1e-6
+    assert ok.sum() >= 3
+    assert relerr(fm.TT[ok], z["TT"][ok]) < TOL
+    assert relerr((fm.T * s)[z["rows"]][:, ok], z["T_rows"][:, ok]) < TOL
+    assert relerr(np.linalg.norm(fm.T, axis=0)[ok], z["T_colnorm"][ok]) < TOL
+    for f in ["P", "R", "W"]:
+        assert relerr((getattr(fm, f) * s)[:, ok], z[f][:, ok]) < TOL, f
+    assert relerr((fm.C * s)[:, ok], z["C"][:, ok]) < TOL
+    # coefficients and predictions at every stored k: always graded (B is well-posed)
+    for i, k in enumerate(z["ks"]):
+        cf = jc.coef(fm, nlv=int(k))
+        assert cf.B.shape == (cfg["p"], cfg["q"]) and cf.int.shape == (1, cfg["q"])
+        if k > 0:
+            assert relerr(cf.B, z["B_ks"][i]) < TOL, k
+        else:
+            assert np.all(cf.B == 0)
+        assert relerr(cf.int, z["int_ks"][i]) < TOL, k
+    pr = jc.predict(fm, Xnew, nlv=range(0, a + 1)).pred
+    assert len(pr) == a + 1
+    for k in range(a + 1):
+        assert relerr(pr[k][z["mrows"]], z["pred_all_rows"][k]) < TOL, k
+    Tn = jc.transform(fm, Xnew)
+    assert relerr((Tn * s)[z["mrows"]][:, ok], z["Tnew_rows"][:, ok]) < TOL
+    single = jc.predict(fm, Xnew).pred                              # nlv = nothing -> one matrix
+    assert relerr(single[z["mrows"]], z["pred_all_rows"][a]) < TOL
+
+
+def test_plskern_bang_writes_back(jc):
+    cfg = dict(n=1000, p=37, q=3, nlv=4, m=10, uniform=False, scal=True)
+    X, Y, w, _ = make_golden.inputs(cfg)
+    Xr, Yr = X.copy(), Y.copy()
+    ref = oracle.plskern_bang(Xr, Yr, w, nlv=4, scal=True)          # reference leaves Xr, Yr scaled
+    fm = jc.plskern_bang(X, Y, w, nlv=4, scal=True)
+    assert relerr(X, Xr) < 1e-12 and relerr(Y, Yr) < 1e-12          # plskern.jl:125-126 side effect
+    s = oracle.sign_align(ref, fm)
+    assert relerr(fm.T * s, ref.T) < TOL
+
+
+def test_invariants_on_device_fit(jc):
+    n, p, q, nlv = 5000, 120, 4, 12
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q) + X[:, :q]
+    w = synth.synth_weights(n, uniform=False)
+    fm = jc.plskern(X, Y, w, nlv=nlv, scal=True)
+    assert abs(fm.weights.sum() - 1) < 1e-13
+    np.testing.assert_allclose(np.linalg.norm(fm.W, axis=0), 1, atol=1e-13)
+    Xc = (X - fm.xmeans) / fm.xscales
+    assert relerr(fm.T, Xc @ fm.R) < 1e-12
+    G = fm.T.T @ (fm.weights[:, None] * fm.T)
+    assert np.abs(G - np.diag(fm.TT)).max() / fm.TT.max() < 1e-12
+    assert np.abs(fm.P.T @ fm.R - np.eye(nlv)).max() < 1e-11
+    Yc = (Y - fm.ymeans) / fm.yscales
+    Cexp = (Yc.T @ (fm.weights[:, None] * fm.T)) / fm.TT
+    assert relerr(fm.C, Cexp) < 1e-11
+
+
+def test_edge_cases(jc):
+    X = synth.synth_matrix(1, 60, 8)
+    Y = synth.synth_matrix(2, 60, 2)
+    fm0 = jc.plskern(X, Y, nlv=0)                                   # nlv = 0 is a valid fit
+    assert fm0.T.shape == (60, 0) and fm0.R.shape == (8, 0)
+    np.testing.assert_allclose(jc.predict(fm0, X[:3]).pred, np.tile(fm0.ymeans, (3, 1)), atol=1e-15)
+    assert jc.transform(fm0, X[:3]).shape == (3, 0)
+    fm = jc.plskern(X, Y[:, 0], nlv=99)                             # vector Y, nlv clamped to min(n,p)
+    assert fm.T.shape == (60, 8) and fm.C.shape == (1, 8)
+    ref = oracle.plskern(X, Y[:, 0], nlv=99)
+    assert relerr(jc.coef(fm).B, oracle.coef(ref)[0]) < 1e-8       # full rank: conditioning-limited
+    pr = jc.predict(fm, X[:4], nlv=[2, 5]).pred                     # widened to 2:5
+    assert len(pr) == 4
+    pr = jc.predict(fm, X[:4], nlv=range(-3, 50)).pred              # clamped to 0:8
+    assert len(pr) == 9
+    r = oracle.predict(ref, X[:4], nlv=range(-3, 50))
+    for k in range(6):
+        assert relerr(pr[k], r[k]) < 1e-9
+    # integer, C-ordered inputs and integer weights are coerced like ensure_mat + Float64.()
+    Xi = (X * 100).astype(np.int64)
+    fmi = jc.plskern(np.ascontiguousarray(Xi), Y, np.arange(1, 61), nlv=1)
+    refi = oracle.plskern(Xi.astype(float), Y, np.arange(1, 61), nlv=1)
+    assert relerr(jc.predict(fmi, Xi[:1]).pred, oracle.predict(refi, Xi[:1].astype(float))) < TOL
+
+
+def test_offset_heavy_data(jc):
+    """Spectra-like data with large column offsets: the pivot + exact correction must not lose digits."""
+    n, p, q, nlv = 4000, 64, 2, 6
+    X = synth.synth_matrix(1, n, p) * 1e-2 + 1e3 + np.arange(p)[None, :] * 10.0
+    Y = synth.synth_matrix(2, n, q) + 5e2
+    fm = jc.plskern(X, Y, nlv=nlv)
+    ref = oracle.plskern(X, Y, nlv=nlv)
+    assert relerr(jc.predict(fm, X[:50]).pred, oracle.predict(ref, X[:50])) < TOL
+    s = oracle.sign_align(ref, fm)
+    assert relerr(fm.T * s, ref.T) < 1e-8     # the oracle's own cancellation floor on this data
+
+
+def test_full_size_properties(jc):
+    """BASELINE C2 at full size (n=1e6, p=500, q=10, nlv=25) through size-independent properties:
+    scores are D-orthogonal with T'DT = diag(TT), P'R = I, ||w|| = 1, T = Xc R on a row sample,
+    and the fit agrees with itself under a row permutation of the inputs."""
+    n, p, q, nlv = 1_000_000, 500, 10, 25
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q)
+    fm = jc.plskern(X, Y, nlv=nlv)
+    np.testing.assert_allclose(np.linalg.norm(fm.W, axis=0), 1, atol=1e-12)
+    G = fm.T.T @ fm.T / n
+    assert np.abs(G - np.diag(fm.TT)).max() / fm.TT.max() < 1e-10
+    assert np.abs(fm.P.T @ fm.R - np.eye(nlv)).max() < 1e-9
+    rows = np.arange(0, n, 997)
+    assert relerr(fm.T[rows], (X[rows] - fm.xmeans) @ fm.R) < 1e-11
+    assert relerr(fm.xmeans, X.mean(axis=0)) < 1e-13
+    perm = np.random.default_rng(0).permutation(n)
+    fm2 = jc.plskern(X[perm], Y[perm], nlv=nlv)
+    assert relerr(jc.coef(fm2).B, jc.coef(fm).B) < TOL
+    s = np.sign(np.sum(fm.W * fm2.W, axis=0))
+    assert relerr((fm2.T * s)[np.argsort(perm)][rows], fm.T[rows]) < 1e-9

@@ -1,0 +1,130 @@
+"""CPU tests of the oracle itself: golden fixtures, the independent NIPALS restatement, algebraic
+invariants of a PLS fit and the counter-based generator."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import make_golden, synth
+from conftest import load_golden, relerr
+
+TOL = 1e-10   # north-star tolerance (relative error on B, T, predictions; sign-aligned LVs)
+
+
+def test_generator_known_answers():
+    # splitmix64-finaliser stream, seeds/counters per SURVEY 8d; values pinned at first implementation
+    u = synth.u01(1, np.arange(4))
+    np.testing.assert_allclose(u, [0.95570382, 0.74868289, 0.82868876, 0.81491197], atol=5e-9)
+    assert np.all((u >= 0) & (u < 1))
+    # python-int restatement of the same recurrence, bit for bit
+    M = (1 << 64) - 1
+
+    def mix(z):
+        z ^= z >> 30; z = (z * 0xBF58476D1CE4E5B9) & M
+        z ^= z >> 27; z = (z * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        return z
+    for s, k in [(1, 0), (2, 12345), (4, 10**12 + 7)]:
+        z = mix((s * 0xD1342543DE82EF95 + (k + 1) * 0x9E3779B97F4A7C15) & M)
+        assert synth.u01(s, np.array([k], dtype=np.uint64))[0] == (z >> 11) * 2.0 ** -53
+
+
+def test_generator_shards_are_slices():
+    full = synth.synth_matrix(1, 100, 7)
+    part = synth.synth_matrix(1, 30, 7, row0=40, n_global=100)
+    assert np.array_equal(full[40:70], part)
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_wscal", "edge_odd", "c2_cut"])
+def test_oracle_reproduces_golden(name):
+    cfg, z = load_golden(name)
+    out = make_golden.run_case(cfg)
+    for key in ["T_rows", "P", "R", "W", "C", "TT", "xmeans", "xscales", "ymeans", "yscales",
+                "B_ks", "int_ks", "pred_all_rows", "Tnew_rows"]:
+        assert relerr(out[key], z[key]) < 1e-12, key
+
+
+@pytest.mark.parametrize("q,scal,uniform", [(1, False, True), (3, True, False), (2, False, False)])
+def test_plskern_equals_nipals(q, scal, uniform):
+    n, p, nlv = 300, 40, 6
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q) + X[:, :q] * 2.0
+    w = synth.synth_weights(n, uniform=uniform)
+    a = oracle.plskern(X, Y, w, nlv=nlv, scal=scal)
+    b = oracle.plsnipals(X, Y, w, nlv=nlv, scal=scal)
+    s = oracle.sign_align(a, b)
+    assert relerr(b.T * s, a.T) < 1e-11
+    assert relerr(b.R * s, a.R) < 1e-11
+    assert relerr(b.P * s, a.P) < 1e-11
+    assert relerr(oracle.coef(b)[0], oracle.coef(a)[0]) < 1e-11
+
+
+def test_invariants():
+    n, p, q, nlv = 200, 30, 3, 8
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q)
+    w = synth.synth_weights(n, uniform=False)
+    fm = oracle.plskern(X, Y, w, nlv=nlv, scal=True)
+    assert abs(fm.weights.sum() - 1) < 1e-14
+    np.testing.assert_allclose(np.linalg.norm(fm.W, axis=0), 1, atol=1e-14)
+    Xc = (X - fm.xmeans) / fm.xscales
+    assert relerr(Xc @ fm.R, fm.T) < 1e-12
+    G = fm.T.T @ (fm.weights[:, None] * fm.T)
+    assert np.abs(G - np.diag(fm.TT)).max() < 1e-14
+    assert np.abs(fm.P.T @ fm.R - np.eye(nlv)).max() < 1e-12
+    # predict(nlv = 0) == ymeans; X untouched by plskern
+    X0 = X.copy()
+    oracle.plskern(X, Y, w, nlv=2)
+    assert np.array_equal(X, X0)
+    pr = oracle.predict(fm, X[:5], nlv=0)
+    np.testing.assert_allclose(pr, np.tile(fm.ymeans, (5, 1)), atol=1e-15)
+    # nlv = rank: weighted least squares
+    fm2 = oracle.plskern(X, Y, w, nlv=p)
+    B, b0 = oracle.coef(fm2)
+    sw = np.sqrt(fm2.weights)[:, None]
+    A = np.hstack([np.ones((n, 1)), X]) * sw
+    sol = np.linalg.lstsq(A, Y * sw, rcond=None)[0]
+    assert relerr(B, sol[1:]) < 1e-8
+
+
+def test_predict_range_semantics():
+    X = synth.synth_matrix(1, 60, 8)
+    Y = synth.synth_matrix(2, 60, 2)
+    fm = oracle.plskern(X, Y, nlv=4)
+    pr = oracle.predict(fm, X[:3], nlv=[1, 3])      # widened to 1:3 (plskern.jl:229)
+    assert isinstance(pr, list) and len(pr) == 3
+    pr = oracle.predict(fm, X[:3], nlv=range(-2, 99))   # clamped to 0:4
+    assert len(pr) == 5
+    assert oracle.predict(fm, X[:3]).shape == (3, 2)    # nothing -> single matrix
+    assert oracle.transform(fm, X[:3], nlv=0).shape == (3, 0)
+    fm0 = oracle.plskern(X, Y, nlv=0)                   # nlv = 0 is a valid fit
+    assert fm0.T.shape == (60, 0)
+    np.testing.assert_allclose(oracle.predict(fm0, X[:2]), np.tile(fm0.ymeans, (2, 1)))
+
+
+def test_longdouble_truth_small():
+    """Extended-precision restatement on a small case: the float64 oracle sits within 1e-12 of it."""
+    n, p, q, nlv = 60, 10, 2, 4
+    X = synth.synth_matrix(1, n, p).astype(np.longdouble)
+    Y = synth.synth_matrix(2, n, q).astype(np.longdouble)
+    w = np.ones(n, dtype=np.longdouble) / n
+    Xc, Yc = X - w @ X, Y - w @ Y
+    XtY = Xc.T @ (w[:, None] * Yc)
+    Rs, Ps, Cs = [], [], []
+    for a in range(nlv):
+        # dominant left singular vector by power iteration in extended precision
+        u = XtY[:, 0].copy()
+        for _ in range(500):
+            u = XtY @ (XtY.T @ u)
+            u /= np.sqrt(u @ u)
+        r = u.copy()
+        for j in range(a):
+            r -= (u @ Ps[j]) * Rs[j]
+        t = Xc @ r
+        tt = t @ (w * t)
+        c = XtY.T @ r / tt
+        zp = Xc.T @ (w * t)
+        XtY = XtY - np.outer(zp, c)
+        Rs.append(r); Ps.append(zp / tt); Cs.append(c)
+    B_ld = (np.stack(Rs, 1) @ np.stack(Cs, 1).T).astype(np.float64)
+    fm = oracle.plskern(X.astype(np.float64), Y.astype(np.float64), nlv=nlv)
+    assert relerr(oracle.coef(fm)[0], B_ld) < 1e-12
