@@ -59,12 +59,17 @@ const char* jcb200_last_error(void);
 /* Bind the library to CUDA device `device` (default 0 on first use). Idempotent. */
 int jcb200_init(int device);
 void jcb200_shutdown(void);
-/* Launch on an external stream (a cudaStream_t, e.g. torch's current stream); NULL = own stream. */
-int jcb200_set_stream(void* cuda_stream);
+/* external != 0: launch on the caller's stream `cuda_stream` (a cudaStream_t; 0 is the legacy default
+ * stream, e.g. torch's current stream); external == 0: back to the library's own stream. */
+int jcb200_set_stream(void* cuda_stream, int32_t external);
 /* Per-phase times (ms) of the last successful call; returns the number of phases written. */
 int jcb200_last_timings(double* ms, int cap);
 /* Synchronise the library stream and collect the phase times of the preceding "_dev" calls. */
 int jcb200_sync_timings(void);
+/* Durations (ms, most recent first) of the last K1 Gram-kernel launches, from CUDA events recorded
+ * around each launch on the launching stream; synchronises that stream.  Returns the count written
+ * (negative/positive status codes on failure are not used here: at most `cap`, at most 256). */
+int jcb200_gram_timings(double* ms, int cap);
 /* Number of kernels this library has launched since load (claim for bench.py's gpu_launches). */
 int64_t jcb200_launch_count(void);
 /* Page-lock / unlock a caller's host array so that the copies run at full PCIe speed. */

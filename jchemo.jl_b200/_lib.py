@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjchemo_b200.so")
+# JCB_LIB selects an alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("JCB_LIB") or os.path.join(HERE, "libjchemo_b200.so")
 
 c_dp = C.POINTER(C.c_double)
 i64, i32 = C.c_int64, C.c_int32
@@ -17,9 +18,10 @@ SIGNATURES = {
     "jcb200_last_error": (C.c_char_p, []),
     "jcb200_init": (C.c_int, [C.c_int]),
     "jcb200_shutdown": (None, []),
-    "jcb200_set_stream": (C.c_int, [C.c_void_p]),
+    "jcb200_set_stream": (C.c_int, [C.c_void_p, i32]),
     "jcb200_last_timings": (C.c_int, [c_dp, C.c_int]),
     "jcb200_sync_timings": (C.c_int, []),
+    "jcb200_gram_timings": (C.c_int, [c_dp, C.c_int]),
     "jcb200_launch_count": (i64, []),
     "jcb200_host_register": (C.c_int, [C.c_void_p, i64]),
     "jcb200_host_unregister": (C.c_int, [C.c_void_p]),
@@ -77,6 +79,13 @@ def check(rc, what):
     if rc != 0:
         msg = lib().jcb200_last_error().decode("utf-8", "replace")
         raise JchemoB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+def gram_timings(k):
+    """Durations (ms) of the last k K1 launches, most recent first."""
+    buf = (C.c_double * k)()
+    n = lib().jcb200_gram_timings(buf, k)
+    return [buf[i] for i in range(max(n, 0))]
 
 
 def last_timings():

@@ -111,6 +111,11 @@ static int init_locked(int device) {
         c->ev_used[i] = false;
         c->last_ms[i] = 0.0;
     }
+    for (int i = 0; i < Ctx::GRAM_RING; ++i) {
+        JCB_CUDA(cudaEventCreate(&c->gram_ev0[i]));
+        JCB_CUDA(cudaEventCreate(&c->gram_ev1[i]));
+    }
+    c->gram_calls = 0;
     c->ready = true;
     return 0;
 }
@@ -226,14 +231,18 @@ void jcb200_shutdown(void) {
         cudaEventDestroy(c->ev_begin[i]);
         cudaEventDestroy(c->ev_end[i]);
     }
+    for (int i = 0; i < Ctx::GRAM_RING; ++i) {
+        cudaEventDestroy(c->gram_ev0[i]);
+        cudaEventDestroy(c->gram_ev1[i]);
+    }
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     c->ready = false;
 }
 
-int jcb200_set_stream(void* cuda_stream) {
+int jcb200_set_stream(void* cuda_stream, int32_t external) {
     API_PROLOGUE();
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    c->stream = external ? (cudaStream_t)cuda_stream : c->own_stream;
     return 0;
 }
 
@@ -242,6 +251,23 @@ int jcb200_last_timings(double* ms, int cap) {
     int nph = cap < JCB200_NPHASE ? cap : JCB200_NPHASE;
     for (int i = 0; i < nph; ++i) ms[i] = g_ctx.last_ms[i];
     return nph;
+}
+
+int jcb200_gram_timings(double* ms, int cap) {
+    API_PROLOGUE();
+    JCB_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t have = c->gram_calls < Ctx::GRAM_RING ? c->gram_calls : Ctx::GRAM_RING;
+    int nout = (int)(have < cap ? have : cap);
+    for (int i = 0; i < nout; ++i) {   // most recent first
+        const int slot = (int)((c->gram_calls - 1 - i) % Ctx::GRAM_RING);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->gram_ev0[slot], c->gram_ev1[slot]) != cudaSuccess) {
+            cudaGetLastError();
+            t = 0.f;
+        }
+        ms[i] = t;
+    }
+    return nout;
 }
 
 int64_t jcb200_launch_count(void) {

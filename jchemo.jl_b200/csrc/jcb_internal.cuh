@@ -61,11 +61,17 @@ struct Ctx {
     // schedule cache key
     int64_t sk_p = -1, sk_q = -1, sk_nst = -1;
     int sk_ngroups = 0, sk_nsegs = 0;
+    int64_t sk_zone_len = 0;
+    size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf solve_ws;
     Buf xmul_ws;
     // general scratch for the host-pointer API
     Buf hX, hY, hW, hT, hSmall, hPred;
+    // per-launch K1 timing ring (bench.py's roofline: average K1 duration over the timed region)
+    static constexpr int GRAM_RING = 256;
+    cudaEvent_t gram_ev0[GRAM_RING], gram_ev1[GRAM_RING];
+    int64_t gram_calls = 0;
     // timing
     cudaEvent_t ev_begin[JCB200_NPHASE], ev_end[JCB200_NPHASE];
     bool ev_used[JCB200_NPHASE];
@@ -143,6 +149,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {   // never blocks
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)

@@ -21,6 +21,8 @@
 //    so every SM is busy for the same time; each piece writes its partial units to a workspace and
 //    K1b sums them in a fixed order (deterministic, no atomics).
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -29,16 +31,24 @@
 
 namespace jcb {
 
-constexpr int KT = 40;                 // rows per pipeline stage
+#ifndef JCB_KT
+#define JCB_KT 56
+#endif
+#ifndef JCB_NSTAGE
+#define JCB_NSTAGE 2
+#endif
+constexpr int KT = JCB_KT;             // rows per pipeline stage (KT % 16 == 8: conflict-free LDS.128)
 constexpr int CB = 32;                 // columns per block
 constexpr int MAXSLOT = 8;             // column blocks staged per stage
-constexpr int NSTAGE = 2;              // pipeline depth
+constexpr int NSTAGE = JCB_NSTAGE;     // pipeline depth
 constexpr int NCW = 16;                // consumer warps per CTA
-constexpr int K1_THREADS = NCW * 32;    // warp 0 / lane 0 doubles as the TMA producer
+constexpr int K1_THREADS = NCW * 32;    // thread 0 doubles as the TMA producer (polls between k8-steps)
 constexpr int UNIT_STRIDE = 1088;      // doubles per partial unit: 1024 G + 32 column sums + sum(w) + pad
-constexpr int SLOT_DOUBLES = CB * KT;  // 1280
+constexpr int SLOT_DOUBLES = CB * KT;
 constexpr int STAGE_BYTES = MAXSLOT * SLOT_DOUBLES * 8 + 512;  // data + weight tile (KT doubles, padded)
-constexpr int K1_SMEM = NSTAGE * STAGE_BYTES + MAXSLOT * CB * 8 + 64;   // + pivot tile + mbarriers
+constexpr int K1_SMEM = NSTAGE * STAGE_BYTES + 64;                     // + mbarriers
+static_assert(KT % 16 == 8, "KT must be 8 mod 16 (bank-conflict-free fragment loads)");
+static_assert(K1_SMEM <= 227 * 1024, "K1 shared memory budget");
 
 struct UnitDesc {
     int8_t sa, sb;      // slots of the A (rows of G) and B (columns of G) blocks
@@ -52,8 +62,34 @@ struct GroupDesc {
     int32_t blk[MAXSLOT];
     UnitDesc unit[NCW];
 };
+// A segment = the share of one group that one CTA accumulates into one partial.  Rows are swept zone by
+// zone (all CTAs are in the same zone at the same time, so the 4 groups that read a column block find
+// it in L2): inside every zone the segment owns the stage offsets [x0, x1) (16.16 fixed point,
+// dithered per zone so that fractional boundaries average out exactly).
 struct SegDesc {
-    int32_t group, s0, s1, pad;
+    int32_t group, pad;
+    int64_t x0, x1;
+};
+
+struct StageIter {
+    int64_t x0, x1, nst;
+    int32_t L, nz, z, cur, end;
+    __device__ __forceinline__ void init(const SegDesc& sd, int64_t nst_, int32_t L_, int32_t nz_) {
+        x0 = sd.x0; x1 = sd.x1; nst = nst_; L = L_; nz = nz_; z = -1; cur = end = 0;
+    }
+    __device__ __forceinline__ bool next(int& st) {
+        while (cur >= end) {
+            if (++z >= nz) return false;
+            const int64_t r = ((int64_t)z * 40503) & 0xFFFF;
+            const int64_t base = (int64_t)z * L;
+            const int64_t lz = min((int64_t)L, nst - base);
+            const int64_t b0 = min((x0 + r) >> 16, lz), b1 = min((x1 + r) >> 16, lz);
+            cur = (int32_t)(base + b0);
+            end = (int32_t)(base + b1);
+        }
+        st = cur++;
+        return true;
+    }
 };
 
 struct GramParams {
@@ -62,61 +98,159 @@ struct GramParams {
     const int32_t* cta_seg;   // [ncta + 1]
     const double* pivot;      // p + q
     double* partials;         // nsegs * NCW * UNIT_STRIDE
-    int64_t n;
+    int64_t n, nst;           // rows, stages
     int32_t p, q, nbx;
     int32_t weighted;
+    int32_t zone_len, nzones; // stages per zone, number of zones
 };
 
 // ------------------------------------------------------------------------------------------ kernel
+// ---------------------------------------------------------------------------------------------
+// Inner loop.  One k8-step of one 32x32 unit: 8 rows of the staged tile, two DMMA k4-halves.
+//  * The A operand (rows of G) is used RAW; only the B operand is centred (and weighted):
+//      acc_ij = sum_k x_ki * w_k (x_kj - c_j)  =  G_ij + c_i s_j ,  s_j = sum_k w_k (x_kj - c_j)
+//    K3 subtracts the rank-one term c_i s_j exactly (s is accumulated by the diagonal units); with the
+//    64K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
+//    compete with DMMA for the FP64 pipe.
+//  * DIAG units skip the 8x8 blocks below the diagonal and accumulate the column sums; NBC < 4 (edge
+//    and Y blocks) skips empty column blocks; MASKED is the zero-filled tail stage of the unweighted
+//    kernel.  All three are COMPILE-TIME: a predicated-off DMMA/DMUL still occupies the FP64 pipe on
+//    sm_100a (measured, profiles/k1_r01_notes.md), so skipped work must not be emitted at all.
+template <bool WEIGHTED, bool DIAG, int NBC, bool MASKED>
+__device__ __forceinline__ void k8_step(const double* __restrict__ tA, const double* __restrict__ tB,
+                                        const double* __restrict__ wt, const double (&pB)[4],
+                                        double (&acc)[4][4][2], double (&bsum)[4], double& wsum,
+                                        const bool sum_w, const int krow, const int rows_valid) {
+    // tA, tB, wt already point at this lane's two rows (krow, krow + 1) of the stage
+    constexpr int MBC = DIAG ? NBC : 4;
+    double2 a[MBC];
+#pragma unroll
+    for (int mb = 0; mb < MBC; ++mb) a[mb] = *reinterpret_cast<const double2*>(tA + mb * 8 * KT);
+    double2 w2 = make_double2(1.0, 1.0);
+    if (WEIGHTED) {
+        w2 = *reinterpret_cast<const double2*>(wt);
+    } else if (MASKED) {
+        w2.x = (krow < rows_valid) ? 1.0 : 0.0;
+        w2.y = (krow + 1 < rows_valid) ? 1.0 : 0.0;
+    }
+    if (DIAG && sum_w) wsum += w2.x + w2.y;
+#pragma unroll
+    for (int nb = 0; nb < NBC; ++nb) {
+        double2 b = *reinterpret_cast<const double2*>(tB + nb * 8 * KT);
+        if (WEIGHTED || MASKED) {
+            b.x = (b.x - pB[nb]) * w2.x;
+            b.y = (b.y - pB[nb]) * w2.y;
+        } else {
+            b.x -= pB[nb];
+            b.y -= pB[nb];
+        }
+        if (DIAG) bsum[nb] += b.x + b.y;
+        // the two k-halves of one accumulator are issued >= 1 DMMA apart (dependent pair)
+#pragma unroll
+        for (int mb = 0; mb < MBC; ++mb)
+            if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b.x);
+#pragma unroll
+        for (int mb = 0; mb < MBC; ++mb)
+            if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b.y);
+    }
+}
+
+// Request side (thread 0 only): the cursor walks this CTA's (segment, stage) list; a request needs its
+// ring slot released by all 16 warps, which thread 0 polls for (never blocking) between k8-steps.
+struct Producer {
+    StageIter iter;
+    int sg, seg_end;
+    int next;         // stage of the pending request, -1 when exhausted
+    uint32_t issued;  // requests issued so far (ring position)
+};
+
 template <bool WEIGHTED>
-__device__ __forceinline__ void compute_stage(const double* __restrict__ tA,
-                                              const double* __restrict__ tB,
-                                              const double* __restrict__ wt,
-                                              const double* __restrict__ pA,
-                                              const double* __restrict__ pB, int g, int kk,
-                                              double (&acc)[4][4][2], double (&bsum)[4],
-                                              double& wsum, const uint32_t mask, const int sums,
-                                              bool masked, int rows_valid) {
-    // mask bit (mb*4+nb) set <=> this 8x8 block of the unit is computed
+__device__ __noinline__ void producer_issue(Producer& P, const GramParams& prm,
+                                            const CUtensorMap* mapX, const CUtensorMap* mapY,
+                                            const CUtensorMap* mapW, unsigned char* smem,
+                                            uint64_t* full) {
+    const int buf = P.issued % NSTAGE;
+    const GroupDesc* gd = &prm.groups[prm.segs[P.sg].group];
+    const int nslots = gd->nslots;
+    const uint32_t bytes = nslots * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
+    mbar_arrive_expect_tx(&full[buf], bytes);
+    unsigned char* base = smem + buf * STAGE_BYTES;
+    const int row0 = P.next * KT;
+    for (int s = 0; s < nslots; ++s) {
+        const int b = gd->blk[s];
+        const bool isy = b >= prm.nbx;
+        tma_load_2d(base + s * SLOT_DOUBLES * 8, isy ? mapY : mapX, row0, (isy ? b - prm.nbx : b) * CB,
+                    &full[buf]);
+    }
+    if (WEIGHTED) tma_load_1d(base + MAXSLOT * SLOT_DOUBLES * 8, mapW, row0, &full[buf]);
+    ++P.issued;
+    // advance the cursor
+    P.next = -1;
+    while (P.sg < P.seg_end) {
+        int st;
+        if (P.iter.next(st)) {
+            P.next = st;
+            break;
+        }
+        if (++P.sg < P.seg_end) P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
+    }
+}
+
+struct K1Shared {
+    unsigned char* smem;
+    uint64_t* full;
+    uint64_t* empty;
+};
+
+// All stages of one segment for one warp-unit variant: a tight loop with the variant dispatch hoisted
+// out (the per-stage bookkeeping is on the critical path: at a stage boundary the four warps of an
+// SMSP leave the DMMA pipe idle together).
+template <bool WEIGHTED, bool DIAG, int NBC>
+__device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u, const GramParams& prm,
+                                            const CUtensorMap* mapX, const CUtensorMap* mapY,
+                                            const CUtensorMap* mapW, const K1Shared sh, Producer& P,
+                                            const bool producer, uint32_t& it, const int g, const int kk,
+                                            const double (&pB)[4], double (&acc)[4][4][2],
+                                            double (&bsum)[4], double& wsum) {
+    const bool sum_w = (u.sums & 2) != 0;
+    const int lane = threadIdx.x & 31;
+    const int offA = u.sa * SLOT_DOUBLES + g * KT + 2 * kk;
+    const int offB = u.sb * SLOT_DOUBLES + g * KT + 2 * kk;
+    StageIter c_iter;
+    c_iter.init(seg, prm.nst, prm.zone_len, prm.nzones);
+    int st;
+    for (; c_iter.next(st); ++it) {
+        const int buf = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        if (producer) {   // the stage about to be consumed must have been requested
+            while (P.issued <= it && P.next >= 0) {
+                mbar_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1);
+                producer_issue<WEIGHTED>(P, prm, mapX, mapY, mapW, sh.smem, sh.full);
+            }
+        }
+        __syncwarp();
+        mbar_wait(&sh.full[buf], ph);
+        const double* base = reinterpret_cast<const double*>(sh.smem + buf * STAGE_BYTES);
+        const double* tA = base + offA;
+        const double* tB = base + offB;
+        const double* wt = base + MAXSLOT * SLOT_DOUBLES + 2 * kk;
+        const int64_t rows_left = prm.n - (int64_t)st * KT;
+        if (!WEIGHTED && rows_left < KT) {
+            for (int k8 = 0; k8 < KT / 8; ++k8)
+                k8_step<WEIGHTED, DIAG, NBC, true>(tA + k8 * 8, tB + k8 * 8, wt + k8 * 8, pB, acc, bsum,
+                                                   wsum, sum_w, k8 * 8 + 2 * kk, (int)rows_left);
+        } else {
 #pragma unroll 1
-    for (int k8 = 0; k8 < KT / 8; ++k8) {
-        const int ko = k8 * 8 + 2 * kk;
-        double2 a[4];
-#pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
-            a[mb] = *reinterpret_cast<const double2*>(tA + (mb * 8 + g) * KT + ko);
-            const double c = pA[mb * 8 + g];
-            a[mb].x -= c;
-            a[mb].y -= c;
-        }
-        double2 w2 = make_double2(1.0, 1.0);
-        if (WEIGHTED) {
-            w2 = *reinterpret_cast<const double2*>(wt + ko);
-        } else if (masked) {
-            w2.x = (ko < rows_valid) ? 1.0 : 0.0;
-            w2.y = (ko + 1 < rows_valid) ? 1.0 : 0.0;
-        }
-        if (sums & 2) wsum += w2.x + w2.y;
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            double2 b = *reinterpret_cast<const double2*>(tB + (nb * 8 + g) * KT + ko);
-            const double c = pB[nb * 8 + g];
-            if (WEIGHTED || masked) {
-                b.x = (b.x - c) * w2.x;
-                b.y = (b.y - c) * w2.y;
-            } else {
-                b.x -= c;
-                b.y -= c;
-            }
-            if (sums & 1) bsum[nb] += b.x + b.y;
-#pragma unroll
-            for (int mb = 0; mb < 4; ++mb) {
-                if (mask & (1u << (mb * 4 + nb))) {
-                    dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b.x);
-                    dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b.y);
-                }
+            for (int k8 = 0; k8 < KT / 8; ++k8) {
+                if (producer && P.next >= 0 && P.issued < it + NSTAGE &&
+                    mbar_test_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1))
+                    producer_issue<WEIGHTED>(P, prm, mapX, mapY, mapW, sh.smem, sh.full);
+                k8_step<WEIGHTED, DIAG, NBC, false>(tA + k8 * 8, tB + k8 * 8, wt + k8 * 8, pB, acc, bsum,
+                                                    wsum, sum_w, 0, KT);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty[buf]);
     }
 }
 
@@ -125,114 +259,103 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
             const __grid_constant__ CUtensorMap mapW, const GramParams prm) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    double* piv_s = reinterpret_cast<double*>(smem + NSTAGE * STAGE_BYTES);   // [MAXSLOT][CB]
-    uint64_t* full = reinterpret_cast<uint64_t*>(piv_s + MAXSLOT * CB);
-    uint64_t* empty = full + NSTAGE;
+    K1Shared sh;
+    sh.smem = smem;
+    sh.full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    sh.empty = sh.full + NSTAGE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCW);
+            mbar_init(&sh.full[s], 1);
+            mbar_init(&sh.empty[s], NCW);
         }
         fence_barrier_init();
     }
     __syncthreads();
     const int seg_begin = prm.cta_seg[blockIdx.x], seg_end = prm.cta_seg[blockIdx.x + 1];
-    const int64_t n = prm.n;
     const bool producer = (threadIdx.x == 0);
 
-    // ---- producer cursor (thread 0 only): next (segment, stage) to request, and its ring position
-    int p_sg = seg_begin, p_st = 0;
-    uint32_t p_it = 0;
-    if (producer && p_sg < seg_end) p_st = prm.segs[p_sg].s0;
-    auto produce_one = [&]() {
-        // requests one stage if any is left; waits for the ring slot to be free first
-        if (p_sg >= seg_end) return;
-        const SegDesc seg = prm.segs[p_sg];
-        const GroupDesc* gd = &prm.groups[seg.group];
-        const int nslots = gd->nslots;
-        const int buf = p_it % NSTAGE;
-        const uint32_t ph = (p_it / NSTAGE) & 1;
-        mbar_wait(&empty[buf], ph ^ 1);
-        const uint32_t bytes = nslots * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
-        mbar_arrive_expect_tx(&full[buf], bytes);
-        unsigned char* base = smem + buf * STAGE_BYTES;
-        const int row0 = p_st * KT;
-        for (int s = 0; s < nslots; ++s) {
-            const int b = gd->blk[s];
-            const bool isy = b >= prm.nbx;
-            tma_load_2d(base + s * SLOT_DOUBLES * 8, isy ? &mapY : &mapX, row0,
-                        (isy ? b - prm.nbx : b) * CB, &full[buf]);
+    Producer P;
+    P.sg = seg_begin;
+    P.seg_end = seg_end;
+    P.next = -1;
+    P.issued = 0;
+    if (producer && seg_begin < seg_end) {
+        P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
+        while (P.sg < P.seg_end) {
+            int st;
+            if (P.iter.next(st)) {
+                P.next = st;
+                break;
+            }
+            if (++P.sg < P.seg_end) P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
         }
-        if (WEIGHTED) tma_load_1d(base + MAXSLOT * SLOT_DOUBLES * 8, &mapW, row0, &full[buf]);
-        ++p_it;
-        if (++p_st >= seg.s1) {
-            ++p_sg;
-            if (p_sg < seg_end) p_st = prm.segs[p_sg].s0;
-        }
-    };
-    if (producer)
-        for (int s = 0; s < NSTAGE; ++s) produce_one();
+        for (int s = 0; s < NSTAGE && P.next >= 0; ++s)
+            producer_issue<WEIGHTED>(P, prm, &mapX, &mapY, &mapW, smem, sh.full);
+    }
 
-    // ---- consumers (all 16 warps)
     const int g = lane >> 2, kk = lane & 3;
     uint32_t it = 0;  // stages consumed by this CTA so far (ring position)
     for (int sg = seg_begin; sg < seg_end; ++sg) {
         const SegDesc seg = prm.segs[sg];
         const GroupDesc* gd = &prm.groups[seg.group];
         const UnitDesc u = gd->unit[warp];
-        // pivots of this group's staged columns (0 for padding columns: TMA zero-fills them)
-        __syncthreads();   // previous segment's readers of piv_s are done
-        for (int e = threadIdx.x; e < MAXSLOT * CB; e += K1_THREADS) {
-            const int s = e / CB, cidx = e - s * CB;
-            double v = 0.0;
-            if (s < gd->nslots) {
-                const int b = gd->blk[s];
-                if (b >= prm.nbx) {
-                    const int col = (b - prm.nbx) * CB + cidx;
-                    if (col < prm.q) v = prm.pivot[prm.p + col];
-                } else {
-                    const int col = b * CB + cidx;
-                    if (col < prm.p) v = prm.pivot[col];
-                }
-            }
-            piv_s[e] = v;
-        }
-        __syncthreads();
-        uint32_t mask = 0;
-#pragma unroll
-        for (int mb = 0; mb < 4; ++mb)
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb)
-                if (u.kind && mb < u.mbc && nb < u.nbc && !(u.kind == 2 && mb > nb))
-                    mask |= 1u << (mb * 4 + nb);
         double acc[4][4][2];
-        double bsum[4];
+        double bsum[4], pB[4];
         double wsum = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             bsum[i] = 0.0;
+            pB[i] = 0.0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         }
-        for (int st = seg.s0; st < seg.s1; ++st, ++it) {
-            const int buf = it % NSTAGE;
-            const uint32_t ph = (it / NSTAGE) & 1;
-            mbar_wait(&full[buf], ph);
-            if (u.kind) {
-                const double* base = reinterpret_cast<const double*>(smem + buf * STAGE_BYTES);
-                const int64_t rows_left = n - (int64_t)st * KT;
-                const bool masked = rows_left < KT;
-                compute_stage<WEIGHTED>(base + u.sa * SLOT_DOUBLES, base + u.sb * SLOT_DOUBLES,
-                                        base + MAXSLOT * SLOT_DOUBLES, piv_s + u.sa * CB,
-                                        piv_s + u.sb * CB, g, kk, acc, bsum, wsum, mask, u.sums,
-                                        masked, masked ? (int)rows_left : KT);
+        if (u.kind) {
+            // pivots of this lane's B columns (0 for padding columns: TMA zero-fills them)
+            const int bb = gd->blk[u.sb];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (bb >= prm.nbx) {
+                    const int col = (bb - prm.nbx) * CB + i * 8 + g;
+                    if (col < prm.q) pB[i] = prm.pivot[prm.p + col];
+                } else {
+                    const int col = bb * CB + i * 8 + g;
+                    if (col < prm.p) pB[i] = prm.pivot[col];
+                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);
-            if (producer) produce_one();   // refill this ring slot once all warps have released it
-            __syncwarp();
         }
+#define JCB_SEG(D, N)                                                                                  \
+    run_segment<WEIGHTED, D, N>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, g, kk, pB, acc, \
+                                bsum, wsum)
+        switch (u.kind ? ((u.kind == 2 ? 4 : 0) + (u.nbc - 1)) : -1) {
+            case 0: JCB_SEG(false, 1); break;
+            case 1: JCB_SEG(false, 2); break;
+            case 2: JCB_SEG(false, 3); break;
+            case 3: JCB_SEG(false, 4); break;
+            case 4: JCB_SEG(true, 1); break;
+            case 5: JCB_SEG(true, 2); break;
+            case 6: JCB_SEG(true, 3); break;
+            case 7: JCB_SEG(true, 4); break;
+            default: {   // idle warp of a small group: keep the ring protocol going
+                StageIter c_iter;
+                c_iter.init(seg, prm.nst, prm.zone_len, prm.nzones);
+                int st;
+                for (; c_iter.next(st); ++it) {
+                    const int buf = it % NSTAGE;
+                    if (producer) {
+                        while (P.issued <= it && P.next >= 0) {
+                            mbar_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1);
+                            producer_issue<WEIGHTED>(P, prm, &mapX, &mapY, &mapW, smem, sh.full);
+                        }
+                    }
+                    __syncwarp();
+                    mbar_wait(&sh.full[buf], (it / NSTAGE) & 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.empty[buf]);
+                }
+            } break;
+        }
+#undef JCB_SEG
         // ---- write this warp's partial unit (fragment order; K1b knows the layout)
         if (u.kind) {
             double* out = prm.partials + ((int64_t)sg * NCW + warp) * UNIT_STRIDE;
@@ -242,7 +365,7 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
                 for (int nb = 0; nb < 4; ++nb)
                     *reinterpret_cast<double2*>(out + ((mb * 4 + nb) * 32 + lane) * 2) =
                         make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-            if (u.sums) {
+            if (u.kind == 2) {
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     double v = bsum[nb];
@@ -280,7 +403,7 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     double* sx = gyy + Q;
     double* sy = sx + P;
     double* sw = sy + Q;
-    const int nelem = 1024 + ((u.sums & 1) ? 32 : 0);
+    const int nelem = 1024 + (u.kind == 2 ? 32 : 0);
     for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
         double s = 0.0;
         for (int sg = sbeg; sg < send; ++sg)
@@ -316,20 +439,35 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     }
 }
 
-// Strided-sample pivot: mean of ~1024 evenly spaced rows per column.  One warp per column.
-__global__ void pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y,
-                             int64_t ldy, int64_t n, int p, int q, double* __restrict__ pivot) {
-    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (col >= p + q) return;
+// Strided-sample pivot: mean of up to 65536 rows per column, taken as 256 evenly spaced chunks of 256
+// consecutive rows (coalesced 2 KB reads).  One block per column.  The pivot only has to be CLOSE to
+// the mean (K3 corrects exactly); a large sample keeps the correction terms c_i s_j and delta delta'
+// far below the rounding level even for offset-heavy data.
+__global__ void __launch_bounds__(256)
+pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+             int64_t n, int p, int q, double* __restrict__ pivot) {
+    const int col = blockIdx.x;
     const double* src = col < p ? X + (int64_t)col * ldx : Y + (int64_t)(col - p) * ldy;
-    const int64_t ns = n < 1024 ? n : 1024;
-    const int64_t stride = n / ns;
+    __shared__ double red[8];
     double s = 0.0;
-    for (int64_t t = lane; t < ns; t += 32) s += src[t * stride];
+    int64_t cnt;
+    if (n <= 65536) {
+        cnt = n;
+        for (int64_t i = threadIdx.x; i < n; i += 256) s += src[i];
+    } else {
+        cnt = 65536;
+        const int64_t stride = n / 256;            // chunk c covers rows [c*stride, c*stride + 256)
+        for (int c = 0; c < 256; ++c) s += src[c * stride + threadIdx.x];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) pivot[col] = s / (double)ns;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        pivot[col] = t / (double)cnt;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -395,11 +533,8 @@ static int make_map_1d(CUtensorMap* map, const double* base, int64_t len, int bo
 
 // Cost of a unit in DMMA pairs per k8-step, used to balance SMSPs and SMs.
 static int unit_cost(const UnitDesc& u) {
-    int c = 0;
-    for (int mb = 0; mb < u.mbc; ++mb)
-        for (int nb = 0; nb < u.nbc; ++nb)
-            if (!(u.kind == 2 && mb > nb)) ++c;
-    return c;
+    if (u.kind == 2) return u.nbc * (u.nbc + 1) / 2;   // upper triangle of nbc x nbc blocks
+    return 4 * u.nbc;                                  // all 4 row blocks x nbc column blocks
 }
 
 struct Schedule {
@@ -411,7 +546,14 @@ struct Schedule {
 };
 
 // Fixed per-stage overhead of a group in the same units as unit_cost (fragment transforms, barrier).
-static double g_stage_overhead = 1.5;
+static double stage_overhead() {
+    static double v = -1;
+    if (v < 0) {
+        const char* e = getenv("JCB_STAGE_OVERHEAD");
+        v = e ? atof(e) : 1.5;
+    }
+    return v;
+}
 
 static void build_groups(int64_t p, int64_t q, Schedule& S) {
     const int nbx = (int)((p + CB - 1) / CB), nby = (int)((q + CB - 1) / CB);
@@ -455,7 +597,7 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
             }
             int mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
             S.groups.push_back(gd);
-            S.gcost.push_back((double)mx + g_stage_overhead);
+            S.gcost.push_back((double)mx + stage_overhead());
         }
     };
     bool sw_assigned = false;
@@ -524,36 +666,37 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
     }
 }
 
-static void build_segments(int64_t nstages, int ncta, Schedule& S) {
+static void build_segments(int64_t nstages, int ncta, int64_t zone_len, Schedule& S) {
     const int ng = (int)S.groups.size();
+    const double L = (double)zone_len;
     double total = 0;
-    for (int g = 0; g < ng; ++g) total += S.gcost[g] * (double)nstages;
+    for (int g = 0; g < ng; ++g) total += S.gcost[g] * L;
     const double share = total / ncta;
     S.segs.clear();
     S.cta_seg.assign(ncta + 1, 0);
     S.group_seg.assign(ng + 1, 0);
-    // walk groups in order; CTA c owns the flattened cost interval [c*share, (c+1)*share)
+    // walk groups in order; CTA c owns the flattened cost interval [c*share, (c+1)*share) of a zone
     std::vector<std::vector<SegDesc>> per_cta(ncta);
+    const int64_t xmax = zone_len << 16;
     double pos = 0;  // flattened cost position of the start of the current group
     for (int g = 0; g < ng; ++g) {
         const double gc = S.gcost[g];
-        const double end = pos + gc * (double)nstages;
-        auto stage_at = [&](int cta) {  // first stage of this group owned by CTA `cta`
+        const double end = pos + gc * L;
+        auto bnd = [&](int cta) {  // stage offset (16.16) where CTA `cta` starts inside this group
             double b = ((double)cta * share - pos) / gc;
-            int64_t sb = (int64_t)(b + 0.5);
-            return std::max<int64_t>(0, std::min<int64_t>(nstages, sb));
+            int64_t xb = (int64_t)llround(b * 65536.0);
+            return std::max<int64_t>(0, std::min<int64_t>(xmax, xb));
         };
         int c_lo = std::min(ncta - 1, (int)(pos / share + 1e-9));
         int c_hi = std::min(ncta - 1, (int)(end / share - 1e-9));
         for (int cta = c_lo; cta <= c_hi; ++cta) {
-            const int64_t s = (cta == c_lo) ? 0 : stage_at(cta);
-            const int64_t e = (cta == c_hi) ? nstages : stage_at(cta + 1);
-            if (e > s) per_cta[cta].push_back(SegDesc{g, (int32_t)s, (int32_t)e, 0});
+            const int64_t x0 = (cta == c_lo) ? 0 : bnd(cta);
+            const int64_t x1 = (cta == c_hi) ? xmax : bnd(cta + 1);
+            if (x1 > x0) per_cta[cta].push_back(SegDesc{g, 0, x0, x1});
         }
         pos = end;
     }
-    // segment order must be group-major for K1b (contiguous per group) and CTA-contiguous for K1:
-    // the walk above already emits both orders at once (CTAs take consecutive pieces).
+    // the walk emits CTA-contiguous (K1) and group-contiguous (K1b) order at once
     for (int c = 0; c < ncta; ++c) {
         S.cta_seg[c] = (int32_t)S.segs.size();
         for (const SegDesc& sd : per_cta[c]) S.segs.push_back(sd);
@@ -565,13 +708,12 @@ static void build_segments(int64_t nstages, int ncta, Schedule& S) {
         while (cur < (int)S.segs.size() && S.segs[cur].group == g) ++cur;
     }
     S.group_seg[ng] = cur;
+    (void)nstages;
 }
 
 int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                  int64_t p, int64_t q, double* d_pivot) {
-    const int warps = 8;
-    const int grid = (int)((p + q + warps - 1) / warps);
-    pivot_kernel<<<grid, warps * 32, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot);
+    pivot_kernel<<<(int)(p + q), 256, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot);
     JCB_LAUNCH_CHECK();
     return 0;
 }
@@ -592,9 +734,23 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     if (c->sk_p != p || c->sk_q != q || c->sk_nst != nstages) {
         Schedule S;
         build_groups(p, q, S);
-        build_segments(nstages, ncta, S);
-        const size_t gb = S.groups.size() * sizeof(GroupDesc), sb = S.segs.size() * sizeof(SegDesc),
-                     cb = S.cta_seg.size() * 4, qb = S.group_seg.size() * 4;
+        // zone = the row range all CTAs sweep together; sized so that one zone of [X Y] (~40 MB) stays
+        // in the 126 MB L2 while the groups that share its column blocks read it.  With more groups
+        // than CTAs there is nothing to co-schedule: one zone.
+        int64_t zone_len = nstages;
+        const char* zenv = getenv("JCB_ZONE_MB");
+        const double zone_mb = zenv ? atof(zenv) : 40.0;
+        if ((int)S.groups.size() * 2 <= ncta && zone_mb > 0) {
+            const int64_t rows = (int64_t)(zone_mb * 1e6 / ((double)(p + q) * 8.0));
+            zone_len = std::max<int64_t>(16, rows / KT);
+            if (zone_len > nstages) zone_len = nstages;
+        }
+        c->sk_zone_len = zone_len;
+        build_segments(nstages, ncta, zone_len, S);
+        auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+        const size_t gb = up16(S.groups.size() * sizeof(GroupDesc)),
+                     sb = up16(S.segs.size() * sizeof(SegDesc)), cb = up16(S.cta_seg.size() * 4),
+                     qb = up16(S.group_seg.size() * 4);
         const size_t tot = gb + sb + cb + qb;
         if (c->sched_host_bytes < tot) {
             if (c->sched_host) cudaFreeHost(c->sched_host);
@@ -605,11 +761,15 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
         // a previous launch may still read the old schedule: drain the stream before overwriting
         JCB_CUDA(cudaStreamSynchronize(c->stream));
         unsigned char* h = (unsigned char*)c->sched_host;
-        memcpy(h, S.groups.data(), gb);
-        memcpy(h + gb, S.segs.data(), sb);
-        memcpy(h + gb + sb, S.cta_seg.data(), cb);
-        memcpy(h + gb + sb + cb, S.group_seg.data(), qb);
+        memset(h, 0, tot);
+        memcpy(h, S.groups.data(), S.groups.size() * sizeof(GroupDesc));
+        memcpy(h + gb, S.segs.data(), S.segs.size() * sizeof(SegDesc));
+        memcpy(h + gb + sb, S.cta_seg.data(), S.cta_seg.size() * 4);
+        memcpy(h + gb + sb + cb, S.group_seg.data(), S.group_seg.size() * 4);
         JCB_CUDA(cudaMemcpyAsync(c->sched_dev.p, h, tot, cudaMemcpyHostToDevice, c->stream));
+        c->sk_off_segs = gb;
+        c->sk_off_cta = gb + sb;
+        c->sk_off_gseg = gb + sb + cb;
         c->sk_p = p;
         c->sk_q = q;
         c->sk_nst = nstages;
@@ -619,10 +779,9 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     const int ng = c->sk_ngroups, nsegs = c->sk_nsegs;
     unsigned char* d = (unsigned char*)c->sched_dev.p;
     const GroupDesc* dgroups = (const GroupDesc*)d;
-    const SegDesc* dsegs = (const SegDesc*)(d + (size_t)ng * sizeof(GroupDesc));
-    const int32_t* dcta = (const int32_t*)(d + (size_t)ng * sizeof(GroupDesc) +
-                                           (size_t)nsegs * sizeof(SegDesc));
-    const int32_t* dgseg = dcta + (ncta + 1);
+    const SegDesc* dsegs = (const SegDesc*)(d + c->sk_off_segs);
+    const int32_t* dcta = (const int32_t*)(d + c->sk_off_cta);
+    const int32_t* dgseg = (const int32_t*)(d + c->sk_off_gseg);
     JCB_TRY(ensure(c->partials, (size_t)nsegs * NCW * UNIT_STRIDE * 8));
 
     CUtensorMap mapX, mapY, mapW;
@@ -640,6 +799,9 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     prm.pivot = d_pivot;
     prm.partials = (double*)c->partials.p;
     prm.n = n;
+    prm.nst = nstages;
+    prm.zone_len = (int32_t)c->sk_zone_len;
+    prm.nzones = (int32_t)((nstages + c->sk_zone_len - 1) / c->sk_zone_len);
     prm.p = (int)p;
     prm.q = (int)q;
     prm.nbx = nbx;
@@ -654,11 +816,15 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
         attr_set = true;
     }
     phase_begin(c, JCB200_T_GRAM);
+    const int slot = (int)(c->gram_calls % Ctx::GRAM_RING);
+    cudaEventRecord(c->gram_ev0[slot], c->stream);
     if (dw)
         gram_kernel<true><<<ncta, K1_THREADS, K1_SMEM, c->stream>>>(mapX, mapY, mapW, prm);
     else
         gram_kernel<false><<<ncta, K1_THREADS, K1_SMEM, c->stream>>>(mapX, mapY, mapW, prm);
     JCB_LAUNCH_CHECK();
+    cudaEventRecord(c->gram_ev1[slot], c->stream);
+    c->gram_calls++;
     phase_end(c, JCB200_T_GRAM);
     phase_begin(c, JCB200_T_REDUCE);
     gram_reduce_kernel<<<ng * NCW, 256, 0, c->stream>>>(dgroups, dgseg, (const double*)c->partials.p,

@@ -46,38 +46,43 @@ __global__ void finalize_stats_kernel(const double* __restrict__ packed,
             const double d = sx[j] / S;
             delta[j] = d;
             xmeans[j] = pivot[j] + d;
-            xscales[j] = scal ? sqrt(gxx[j + (int64_t)j * P] / S - d * d) : 1.0;
+            // K1 leaves acc_jj = G_jj + c_j s_j (A operand raw): remove the rank-one term first
+            xscales[j] = scal ? sqrt((gxx[j + (int64_t)j * P] - pivot[j] * sx[j]) / S - d * d) : 1.0;
         } else {
             const int k = j - p;
             const double d = sy[k] / S;
             delta[j] = d;
             ymeans[k] = pivot[j] + d;
-            yscales[k] = scal ? sqrt(gyy[k] / S - d * d) : 1.0;
+            yscales[k] = scal ? sqrt((gyy[k] - pivot[j] * sy[k]) / S - d * d) : 1.0;
         }
     }
 }
 
 // XtX (full, mirrored) and XtY, centred exactly and scaled
 __global__ void finalize_gram_kernel(const double* __restrict__ packed,
+                                     const double* __restrict__ pivot,
                                      const double* __restrict__ delta,
                                      const double* __restrict__ xscales,
                                      const double* __restrict__ yscales, int p, int q,
                                      double* __restrict__ XtX, double* __restrict__ XtY) {
     const int64_t P = p, Q = q;
-    const double S = packed[P * P + P * Q + Q + P + Q];
+    const double* sx = packed + P * P + P * Q + Q;
+    const double* sy = sx + P;
+    const double S = sy[Q];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // row
     const int j = blockIdx.y;                              // column of [XtX | XtY]
     if (i >= p) return;
     if (j < p) {
         if (i > j) return;
-        const double v = (packed[i + (int64_t)j * P] / S - delta[i] * delta[j]) /
+        // K1: acc_ij = G_ij + c_i s_j (A operand raw, B operand centred about the pivot c)
+        const double v = ((packed[i + (int64_t)j * P] - pivot[i] * sx[j]) / S - delta[i] * delta[j]) /
                          (xscales[i] * xscales[j]);
         XtX[i + (int64_t)j * P] = v;
         XtX[j + (int64_t)i * P] = v;
     } else {
         const int k = j - p;
         XtY[i + (int64_t)k * P] =
-            (packed[P * P + i + (int64_t)k * P] / S - delta[i] * delta[p + k]) /
+            ((packed[P * P + i + (int64_t)k * P] - pivot[i] * sy[k]) / S - delta[i] * delta[p + k]) /
             (xscales[i] * yscales[k]);
     }
 }
@@ -103,15 +108,48 @@ __device__ double block_sum(double v, double* red) {
 
 struct LvParams {
     const double* XtX;   // p x p, symmetric, read only
-    double* XtY;         // p x q, deflated in place
-    double* zp;          // p, exchange buffer
+    double* XtY;         // p x q (K3 output); deflated in place only when it does not fit in smem
+    double* zp;          // 2 * p, exchange buffer (double-buffered by LV parity)
     double* P;
     double* R;
     double* W;
     double* C;
     double* TT;
     int p, q, nlv;
+    int xty_smem;        // XtY resident in shared memory (every CTA deflates its own full copy)
+    double* Ppriv;       // LV_CLUSTER private copies of P and R (p x nlv each): with XtY in smem a CTA
+    double* Rpriv;       // reads back only what it wrote itself, so one cluster barrier per LV suffices
 };
+
+// dot of a shared vector with a global column, lanes strided, 8 independent loads in flight
+__device__ __forceinline__ double warp_dot_gs(const double* __restrict__ gcol,
+                                              const double* __restrict__ svec, int p, int lane) {
+    double s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.0;
+    int k = lane;
+    for (; k + 7 * 32 < p; k += 8 * 32) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(gcol + k + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[u] * svec[k + u * 32];
+    }
+    for (; k < p; k += 32) s[0] += __ldcg(gcol + k) * svec[k];
+    return warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+}
+
+__device__ __forceinline__ double warp_dot_ss(const double* __restrict__ a,
+                                              const double* __restrict__ b, int p, int lane) {
+    double s0 = 0.0, s1 = 0.0;
+    int k = lane;
+    for (; k + 32 < p; k += 64) {
+        s0 += a[k] * b[k];
+        s1 += a[k + 32] * b[k + 32];
+    }
+    if (k < p) s0 += a[k] * b[k];
+    return warp_sum(s0 + s1);
+}
 
 __global__ void __cluster_dims__(LV_CLUSTER, 1, 1) __launch_bounds__(LV_THREADS, 1)
 lvloop_kernel(const LvParams prm) {
@@ -128,20 +166,28 @@ lvloop_kernel(const LvParams prm) {
     double* c_s = v_s + q;        // q
     double* d_s = c_s + q;        // nlv (dots w'P_j)
     double* red = d_s + nlv;      // 64
-    __shared__ int flag_s;
+    double* xty_s = red + 64;     // p*q when prm.xty_smem
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = LV_THREADS >> 5;
     const int rank = (int)cluster.block_rank();
     const int per = (p + LV_CLUSTER - 1) / LV_CLUSTER;
     const int lo = min(p, rank * per), hi = min(p, lo + per);
     const int64_t P64 = p;
+    const bool xs = prm.xty_smem != 0;
+    const double* Pr = xs ? prm.Ppriv + (int64_t)rank * P64 * nlv : prm.P;   // where this CTA reads P, R
+    const double* Rr = xs ? prm.Rpriv + (int64_t)rank * P64 * nlv : prm.R;
+    // column j of XtY: shared copy, or global (L2) when it does not fit
+    if (xs) {
+        for (int e = tid; e < p * q; e += LV_THREADS) xty_s[e] = prm.XtY[e];
+        __syncthreads();
+    }
 
     for (int a = 0; a < nlv; ++a) {
         // ---------------------------------------------------------------- (1) weight vector w
         if (q == 1) {
             double s = 0.0;
             for (int k = tid; k < p; k += LV_THREADS) {
-                const double x = __ldcg(prm.XtY + k);
+                const double x = xs ? xty_s[k] : __ldcg(prm.XtY + k);
                 w_s[k] = x;
                 s += x * x;
             }
@@ -154,41 +200,79 @@ lvloop_kernel(const LvParams prm) {
                 int i = 0, rem = pr;
                 while (rem >= q - i) { rem -= q - i; ++i; }
                 const int j = i + rem;
-                const double* ci = prm.XtY + (int64_t)i * P64;
-                const double* cj = prm.XtY + (int64_t)j * P64;
-                double s = 0.0;
-                for (int k = lane; k < p; k += 32) s += __ldcg(ci + k) * __ldcg(cj + k);
-                s = warp_sum(s);
+                double s;
+                if (xs) {
+                    s = warp_dot_ss(xty_s + (int64_t)i * P64, xty_s + (int64_t)j * P64, p, lane);
+                } else {
+                    const double* ci = prm.XtY + (int64_t)i * P64;
+                    const double* cj = prm.XtY + (int64_t)j * P64;
+                    double s0 = 0.0, s1 = 0.0;
+                    int k = lane;
+                    for (; k + 32 < p; k += 64) {
+                        const double a0 = __ldcg(ci + k), b0 = __ldcg(cj + k);
+                        const double a1 = __ldcg(ci + k + 32), b1 = __ldcg(cj + k + 32);
+                        s0 += a0 * b0;
+                        s1 += a1 * b1;
+                    }
+                    if (k < p) s0 += __ldcg(ci + k) * __ldcg(cj + k);
+                    s = warp_sum(s0 + s1);
+                }
                 if (lane == 0) { M_s[i * q + j] = s; M_s[j * q + i] = s; }
             }
             __syncthreads();
-            // dominant eigenvector by repeated squaring of the trace-normalised matrix
-            double tr = 0.0;
-            for (int i = 0; i < q; ++i) tr += M_s[i * q + i];
-            for (int e = tid; e < q * q; e += LV_THREADS) A_s[e] = M_s[e] / tr;
-            __syncthreads();
-            for (int iter = 0; iter < 64; ++iter) {
-                for (int e = tid; e < q * q; e += LV_THREADS) {
-                    const int i = e / q, j = e - i * q;
-                    double s = 0.0;
-                    for (int k = 0; k < q; ++k) s += A_s[i * q + k] * A_s[k * q + j];
-                    B_s[e] = s;
+            // dominant eigenvector by repeated squaring of the trace-normalised matrix:
+            // A <- A*A / tr(A*A) converges quadratically to v v' (tr(A*A) = ||A||_F^2, A symmetric).
+            // One thread per entry, two named barriers per squaring among the warps that hold entries.
+            // Once the largest change drops below 1e-12 the contamination is below 1e-24 one squaring
+            // later; two more are done for margin.
+            {
+                const int qq = q * q;
+                const int ew = min(nwarp, (qq + 31) / 32);          // warps that take part
+                const int eth = ew * 32;
+                if (warp < ew) {
+                    double tr = 0.0;
+                    for (int i = 0; i < q; ++i) tr += M_s[i * q + i];
+                    for (int e = tid; e < qq; e += eth) A_s[e] = M_s[e] / tr;
+                    asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
+                    int extra = 0;
+                    for (int iter = 0; iter < 80; ++iter) {
+                        double sq = 0.0;
+                        for (int e = tid; e < qq; e += eth) {
+                            const int i = e / q, j = e - i * q;
+                            const double* ai = A_s + i * q;
+                            const double* aj = A_s + j;
+                            double s0 = 0.0, s1 = 0.0;
+                            int k = 0;
+                            for (; k + 1 < q; k += 2) {
+                                s0 += ai[k] * aj[k * q];
+                                s1 += ai[k + 1] * aj[(k + 1) * q];
+                            }
+                            if (k < q) s0 += ai[k] * aj[k * q];
+                            B_s[e] = s0 + s1;
+                            const double aij = ai[j];
+                            sq += aij * aij;
+                        }
+                        sq = warp_sum(sq);
+                        if (lane == 0) red[warp] = sq;
+                        asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
+                        double t2 = 0.0;
+                        for (int w2 = 0; w2 < ew; ++w2) t2 += red[w2];
+                        double chg = 0.0;
+                        for (int e = tid; e < qq; e += eth) {
+                            const double nv = B_s[e] / t2;
+                            chg = fmax(chg, fabs(nv - A_s[e]));
+                            A_s[e] = nv;
+                        }
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) chg = fmax(chg, __shfl_xor_sync(0xffffffffu, chg, o));
+                        if (lane == 0) red[32 + warp] = chg;
+                        asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
+                        double cmax = 0.0;
+                        for (int w2 = 0; w2 < ew; ++w2) cmax = fmax(cmax, red[32 + w2]);
+                        if (cmax < 1e-12 && ++extra == 3) break;
+                    }
                 }
-                if (tid == 0) flag_s = 0;
                 __syncthreads();
-                double t2 = 0.0;
-                for (int i = 0; i < q; ++i) t2 += B_s[i * q + i];
-                bool moved = false;
-                for (int e = tid; e < q * q; e += LV_THREADS) {
-                    const double nv = B_s[e] / t2;
-                    if (fabs(nv - A_s[e]) > 1e-15) moved = true;
-                    A_s[e] = nv;
-                }
-                if (moved) flag_s = 1;
-                __syncthreads();
-                const int f = flag_s;
-                __syncthreads();
-                if (!f) break;
             }
             // v = column with the largest diagonal entry, then two refining power steps on M
             if (warp == 0) {
@@ -219,7 +303,11 @@ lvloop_kernel(const LvParams prm) {
             double s = 0.0;
             for (int k = tid; k < p; k += LV_THREADS) {
                 double t = 0.0;
-                for (int j = 0; j < q; ++j) t += __ldcg(prm.XtY + k + (int64_t)j * P64) * v_s[j];
+                if (xs) {
+                    for (int j = 0; j < q; ++j) t += xty_s[k + (int64_t)j * P64] * v_s[j];
+                } else {
+                    for (int j = 0; j < q; ++j) t += __ldcg(prm.XtY + k + (int64_t)j * P64) * v_s[j];
+                }
                 w_s[k] = t;
                 s += t * t;
             }
@@ -229,38 +317,48 @@ lvloop_kernel(const LvParams prm) {
         __syncthreads();
         // ---------------------------------------------------------------- (2) r
         for (int j = warp; j < a; j += nwarp) {
-            const double* pj = prm.P + (int64_t)j * P64;
-            double s = 0.0;
-            for (int k = lane; k < p; k += 32) s += w_s[k] * __ldcg(pj + k);
-            s = warp_sum(s);
+            const double s = warp_dot_gs(Pr + (int64_t)j * P64, w_s, p, lane);
             if (lane == 0) d_s[j] = s;
         }
         __syncthreads();
         for (int k = tid; k < p; k += LV_THREADS) {
             double rv = w_s[k];
-            for (int j = 0; j < a; ++j) rv -= d_s[j] * __ldcg(prm.R + k + (int64_t)j * P64);
+            int j = 0;
+            for (; j + 8 <= a; j += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(Rr + k + (int64_t)(j + u) * P64);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) rv -= d_s[j + u] * v[u];
+            }
+            for (; j < a; ++j) rv -= d_s[j] * __ldcg(Rr + k + (int64_t)j * P64);
             r_s[k] = rv;
         }
         __syncthreads();
         // ---------------------------------------------------------------- (3) zp slice = XtX[lo:hi, :] r
+        double* zp_g = prm.zp + (a & 1) * P64;
         for (int i = lo + warp; i < hi; i += nwarp) {
             const double* row = prm.XtX + (int64_t)i * P64;   // symmetric: row i == column i
-            double s0 = 0.0, s1 = 0.0;
+            double s[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] = 0.0;
             int k = lane;
-            for (; k + 32 < p; k += 64) {
-                s0 += row[k] * r_s[k];
-                s1 += row[k + 32] * r_s[k + 32];
+            for (; k + 7 * 32 < p; k += 8 * 32) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = row[k + u * 32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s[u] += v[u] * r_s[k + u * 32];
             }
-            if (k < p) s0 += row[k] * r_s[k];
-            const double s = warp_sum(s0 + s1);
-            if (lane == 0) __stcg(prm.zp + i, s);
+            for (; k < p; k += 32) s[0] += row[k] * r_s[k];
+            const double t = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+            if (lane == 0) __stcg(zp_g + i, t);
         }
         // u = XtY' r (pre-deflation XtY; c = u / tt once tt is known)
         for (int j = warp; j < q; j += nwarp) {
-            const double* cj = prm.XtY + (int64_t)j * P64;
-            double t = 0.0;
-            for (int k = lane; k < p; k += 32) t += __ldcg(cj + k) * r_s[k];
-            t = warp_sum(t);
+            double t;
+            if (xs) t = warp_dot_ss(xty_s + (int64_t)j * P64, r_s, p, lane);
+            else t = warp_dot_gs(prm.XtY + (int64_t)j * P64, r_s, p, lane);
             if (lane == 0) c_s[j] = t;
         }
         // barrier 1: zp slices visible; every CTA has finished reading the pre-deflation XtY
@@ -268,7 +366,7 @@ lvloop_kernel(const LvParams prm) {
         // ---------------------------------------------------------------- (4) tt, c
         double s = 0.0;
         for (int k = tid; k < p; k += LV_THREADS) {
-            const double z = __ldcg(prm.zp + k);
+            const double z = __ldcg(zp_g + k);
             zp_s[k] = z;
             s += r_s[k] * z;
         }
@@ -276,12 +374,20 @@ lvloop_kernel(const LvParams prm) {
         __syncthreads();
         for (int j = tid; j < q; j += LV_THREADS) c_s[j] /= tt;
         __syncthreads();
-        // ---------------------------------------------------------------- (5) deflate own slice, store
-        const int nsl = hi - lo;
-        for (int e = tid; e < nsl * q; e += LV_THREADS) {
-            const int j = e / nsl, i = lo + (e - j * nsl);
-            double* dst = prm.XtY + i + (int64_t)j * P64;
-            __stcg(dst, __ldcg(dst) - zp_s[i] * c_s[j]);
+        // ---------------------------------------------------------------- (5) deflate, store
+        if (xs) {
+            // every CTA deflates its own full shared copy (bit-identical everywhere)
+            for (int e = tid; e < p * q; e += LV_THREADS) {
+                const int j = e / p, i = e - j * p;
+                xty_s[e] -= zp_s[i] * c_s[j];
+            }
+        } else {
+            const int nsl = hi - lo;
+            for (int e = tid; e < nsl * q; e += LV_THREADS) {
+                const int j = e / nsl, i = lo + (e - j * nsl);
+                double* dst = prm.XtY + i + (int64_t)j * P64;
+                __stcg(dst, __ldcg(dst) - zp_s[i] * c_s[j]);
+            }
         }
         for (int i = lo + tid; i < hi; i += LV_THREADS) {
             __stcg(prm.P + i + (int64_t)a * P64, zp_s[i] / tt);
@@ -292,8 +398,19 @@ lvloop_kernel(const LvParams prm) {
             for (int j = tid; j < q; j += LV_THREADS) prm.C[j + (int64_t)a * q] = c_s[j];
             if (tid == 0) prm.TT[a] = tt;
         }
-        // barrier 2: deflated XtY and columns a of P, R visible to the whole cluster
-        cluster.sync();
+        if (xs) {
+            // private full columns a of P and R; only this CTA reads them back (next LVs)
+            double* Pw = prm.Ppriv + (int64_t)rank * P64 * nlv + (int64_t)a * P64;
+            double* Rw = prm.Rpriv + (int64_t)rank * P64 * nlv + (int64_t)a * P64;
+            for (int i = tid; i < p; i += LV_THREADS) {
+                __stcg(Pw + i, zp_s[i] / tt);
+                __stcg(Rw + i, r_s[i]);
+            }
+            __syncthreads();
+        } else {
+            // barrier 2: columns a of P, R and the deflated global XtY visible to the whole cluster
+            cluster.sync();
+        }
     }
 }
 
@@ -301,20 +418,22 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
                  int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
                  double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
                  double* dsumw) {
-    // workspace: XtX p*p | XtY p*q | delta p+q | zp p
-    const size_t need = (size_t)(p * p + p * q + (p + q) + p) * 8;
+    // workspace: XtX p*p | XtY p*q | delta p+q | zp 2p | Ppriv, Rpriv LV_CLUSTER*p*nlv each
+    const size_t need = (size_t)(p * p + p * q + (p + q) + 2 * p + 2 * (size_t)LV_CLUSTER * p * nlv) * 8;
     JCB_TRY(ensure(c->solve_ws, need));
     double* XtX = (double*)c->solve_ws.p;
     double* XtY = XtX + p * p;
     double* delta = XtY + p * q;
     double* zp = delta + (p + q);
+    double* Ppriv = zp + 2 * p;
+    double* Rpriv = Ppriv + (size_t)LV_CLUSTER * p * nlv;
 
     phase_begin(c, JCB200_T_FINALIZE);
     finalize_stats_kernel<<<(int)((p + q + 255) / 256), 256, 0, c->stream>>>(
         d_packed, d_pivot, (int)p, (int)q, scal, dxmeans, dxscales, dymeans, dyscales, dsumw, delta);
     JCB_LAUNCH_CHECK();
     dim3 grid((unsigned)((p + 127) / 128), (unsigned)(p + q));
-    finalize_gram_kernel<<<grid, 128, 0, c->stream>>>(d_packed, delta, dxscales, dyscales, (int)p,
+    finalize_gram_kernel<<<grid, 128, 0, c->stream>>>(d_packed, d_pivot, delta, dxscales, dyscales, (int)p,
                                                       (int)q, XtX, XtY);
     JCB_LAUNCH_CHECK();
     phase_end(c, JCB200_T_FINALIZE);
@@ -332,7 +451,11 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
     prm.p = (int)p;
     prm.q = (int)q;
     prm.nlv = nlv;
-    const size_t smem = (size_t)(3 * p + 3 * q * q + 2 * q + nlv + 64) * 8;
+    prm.Ppriv = Ppriv;
+    prm.Rpriv = Rpriv;
+    size_t smem = (size_t)(3 * p + 3 * q * q + 2 * q + nlv + 64) * 8;
+    prm.xty_smem = (smem + (size_t)p * q * 8 <= 160 * 1024) ? 1 : 0;
+    if (prm.xty_smem) smem += (size_t)p * q * 8;
     if (smem > 200 * 1024) {
         set_error("solve: p=%lld q=%lld need %zu bytes of shared memory (> 200 KB)", (long long)p,
                   (long long)q, smem);

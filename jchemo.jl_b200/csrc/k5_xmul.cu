@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int64_t row0 = t * XM_MT;
             const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
-            const bool bulk = prm.aligned && rows == XM_MT;
+            // aligned shards have an even leading dimension, so a ragged last tile may copy one padding
+            // row (rows rounded up to even: bulk copies move multiples of 16 bytes) and stay in bounds
+            const bool bulk = prm.aligned != 0;
+            const int crow = (rows + 1) & ~1;
             for (int ch = 0; ch < nchunk; ++ch, ++it) {
                 const int buf = it % nstage;
                 const uint32_t ph = (it / nstage) & 1;
@@ -112,11 +115,11 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                 double* ms = xs + XM_KC * XM_PITCH;
                 const double* msrc = prm.Mt + (int64_t)ch * NP * XM_MPITCH;
                 if (bulk) {
-                    if (lane == 0) mbar_arrive_expect_tx(&full[buf], XM_KC * XM_MT * 8 + MBYTES);
+                    if (lane == 0) mbar_arrive_expect_tx(&full[buf], XM_KC * crow * 8 + MBYTES);
                     __syncwarp();
                     const int k = ch * XM_KC + lane;
                     const double* src = k < prm.p ? prm.X + row0 + (int64_t)k * prm.ldx : prm.zeros;
-                    bulk_load(xs + lane * XM_PITCH, src, XM_MT * 8, &full[buf]);
+                    bulk_load(xs + lane * XM_PITCH, src, crow * 8, &full[buf]);
                     if (lane == 0) bulk_load(ms, msrc, MBYTES, &full[buf]);
                 } else {
                     // ragged / unaligned tile: plain loads through registers

@@ -27,8 +27,12 @@ def colmajor_empty(n, p, device="cuda"):
 
 def use_current_stream():
     """Launch the library's kernels on torch's current stream (so torch.cuda.Event sees them)."""
-    _lib.check(_lib.lib().jcb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+    _lib.check(_lib.lib().jcb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1),
                "set_stream")
+
+
+def use_own_stream():
+    _lib.check(_lib.lib().jcb200_set_stream(None, 0), "set_stream")
 
 
 def init(device_index):
