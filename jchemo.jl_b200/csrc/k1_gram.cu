@@ -58,7 +58,8 @@ struct UnitDesc {
     int8_t pad[2];
 };
 struct GroupDesc {
-    int32_t nslots;
+    int32_t nslots;           // 4 * nranges: range r = blocks blk[4r .. 4r+3] (consecutive; -1 = unused)
+    int32_t nranges;
     int32_t blk[MAXSLOT];
     UnitDesc unit[NCW];
 };
@@ -102,6 +103,9 @@ struct GramParams {
     int32_t p, q, nbx;
     int32_t weighted;
     int32_t zone_len, nzones; // stages per zone, number of zones
+#ifdef JCB_K1_TRACE
+    long long* trace;         // debug builds: [cta < 4][stage < 64][warp][3] clock64 stamps
+#endif
 };
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -116,42 +120,78 @@ struct GramParams {
 //    and Y blocks) skips empty column blocks; MASKED is the zero-filled tail stage of the unweighted
 //    kernel.  All three are COMPILE-TIME: a predicated-off DMMA/DMUL still occupies the FP64 pipe on
 //    sm_100a (measured, profiles/k1_r01_notes.md), so skipped work must not be emitted at all.
-template <bool WEIGHTED, bool DIAG, int NBC, bool MASKED>
-__device__ __forceinline__ void k8_step(const double* __restrict__ tA, const double* __restrict__ tB,
-                                        const double* __restrict__ wt, const double (&pB)[4],
-                                        double (&acc)[4][4][2], double (&bsum)[4], double& wsum,
-                                        const bool sum_w, const int krow, const int rows_valid) {
-    // tA, tB, wt already point at this lane's two rows (krow, krow + 1) of the stage
+// All k8-steps of one stage of one 32x32 unit.  Per k8-step: A fragments (raw), then the B fragments
+// NG column blocks at a time (centred, weighted; diagonal units also accumulate the column sums).
+// Within a group all first k-halves are issued before any second half, so the two dependent DMMAs of
+// an accumulator are >= 8 (full) or >= 10 (diagonal) issue slots apart.
+// (A register-level software pipeline of the B transform was tried and was slower: 128 registers.)
+template <bool WEIGHTED, bool DIAG, int NBC, bool MASKED, typename Poll>
+__device__ __forceinline__ void stage_steps(const double* __restrict__ tA, const double* __restrict__ tB,
+                                            const double* __restrict__ wt, const double (&pB)[4],
+                                            double (&acc)[4][4][2], double (&bsum)[4], double& wsum,
+                                            const bool sum_w, const int krow0, const int rows_valid,
+                                            Poll& poll) {
     constexpr int MBC = DIAG ? NBC : 4;
-    double2 a[MBC];
+    constexpr int NG = DIAG ? NBC : (NBC >= 2 ? 2 : 1);
+#pragma unroll 1
+    for (int k8 = 0; k8 < KT / 8; ++k8) {
+        poll();
+        double2 a[MBC];
 #pragma unroll
-    for (int mb = 0; mb < MBC; ++mb) a[mb] = *reinterpret_cast<const double2*>(tA + mb * 8 * KT);
-    double2 w2 = make_double2(1.0, 1.0);
-    if (WEIGHTED) {
-        w2 = *reinterpret_cast<const double2*>(wt);
-    } else if (MASKED) {
-        w2.x = (krow < rows_valid) ? 1.0 : 0.0;
-        w2.y = (krow + 1 < rows_valid) ? 1.0 : 0.0;
-    }
-    if (DIAG && sum_w) wsum += w2.x + w2.y;
-#pragma unroll
-    for (int nb = 0; nb < NBC; ++nb) {
-        double2 b = *reinterpret_cast<const double2*>(tB + nb * 8 * KT);
-        if (WEIGHTED || MASKED) {
-            b.x = (b.x - pB[nb]) * w2.x;
-            b.y = (b.y - pB[nb]) * w2.y;
-        } else {
-            b.x -= pB[nb];
-            b.y -= pB[nb];
+        for (int mb = 0; mb < MBC; ++mb)
+            a[mb] = *reinterpret_cast<const double2*>(tA + k8 * 8 + mb * 8 * KT);
+        double2 w2 = make_double2(1.0, 1.0);
+        if (WEIGHTED) {
+            w2 = *reinterpret_cast<const double2*>(wt + k8 * 8);
+        } else if (MASKED) {
+            w2.x = (krow0 + k8 * 8 < rows_valid) ? 1.0 : 0.0;
+            w2.y = (krow0 + k8 * 8 + 1 < rows_valid) ? 1.0 : 0.0;
         }
-        if (DIAG) bsum[nb] += b.x + b.y;
-        // the two k-halves of one accumulator are issued >= 1 DMMA apart (dependent pair)
+        if (DIAG && sum_w) wsum += w2.x + w2.y;
 #pragma unroll
-        for (int mb = 0; mb < MBC; ++mb)
-            if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b.x);
+        for (int n0 = 0; n0 < NBC; n0 += NG) {
+            double2 b[NG];
 #pragma unroll
-        for (int mb = 0; mb < MBC; ++mb)
-            if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b.y);
+            for (int j = 0; j < NG; ++j) {
+                const int nb = n0 + j;
+                if (nb < NBC) {
+                    b[j] = *reinterpret_cast<const double2*>(tB + k8 * 8 + nb * 8 * KT);
+                    if (WEIGHTED || MASKED) {
+                        b[j].x = (b[j].x - pB[nb]) * w2.x;
+                        b[j].y = (b[j].y - pB[nb]) * w2.y;
+                    } else {
+                        b[j].x -= pB[nb];
+                        b[j].y -= pB[nb];
+                    }
+                    if (DIAG) {
+                        // column sums ride in the accumulator blocks below the diagonal, which a
+                        // diagonal unit never uses: two independent DADD chains per column block
+                        // (a dependent DADD pair would stall this warp behind the other warps' DMMAs)
+                        double(&sx)[2] = nb < 3 ? acc[3][nb] : acc[2][0];
+                        sx[0] += b[j].x;
+                        sx[1] += b[j].y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const int nb = n0 + j;
+                if (nb < NBC) {
+#pragma unroll
+                    for (int mb = 0; mb < MBC; ++mb)
+                        if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[j].x);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const int nb = n0 + j;
+                if (nb < NBC) {
+#pragma unroll
+                    for (int mb = 0; mb < MBC; ++mb)
+                        if (!DIAG || mb <= nb) dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[j].y);
+                }
+            }
+        }
     }
 }
 
@@ -162,7 +202,35 @@ struct Producer {
     int sg, seg_end;
     int next;         // stage of the pending request, -1 when exhausted
     uint32_t issued;  // requests issued so far (ring position)
+    // cached description of the current segment's group: up to 2 ranges of <= 4 consecutive blocks,
+    // range r always lands in ring slots [4r, 4r + 4) with ONE 128-column TMA box
+    int nranges, col[2], isy[2];
 };
+
+__device__ __forceinline__ void producer_load_group(Producer& P, const GramParams& prm) {
+    const GroupDesc* gd = &prm.groups[prm.segs[P.sg].group];
+    P.nranges = gd->nranges;
+    for (int r = 0; r < 2; ++r) {
+        const int b = gd->blk[4 * r];
+        P.isy[r] = b >= prm.nbx;
+        P.col[r] = (P.isy[r] ? b - prm.nbx : b) * CB;
+    }
+}
+
+__device__ __forceinline__ void producer_advance(Producer& P, const GramParams& prm) {
+    P.next = -1;
+    while (P.sg < P.seg_end) {
+        int st;
+        if (P.iter.next(st)) {
+            P.next = st;
+            return;
+        }
+        if (++P.sg < P.seg_end) {
+            P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
+            producer_load_group(P, prm);
+        }
+    }
+}
 
 template <bool WEIGHTED>
 __device__ __noinline__ void producer_issue(Producer& P, const GramParams& prm,
@@ -170,30 +238,16 @@ __device__ __noinline__ void producer_issue(Producer& P, const GramParams& prm,
                                             const CUtensorMap* mapW, unsigned char* smem,
                                             uint64_t* full) {
     const int buf = P.issued % NSTAGE;
-    const GroupDesc* gd = &prm.groups[prm.segs[P.sg].group];
-    const int nslots = gd->nslots;
-    const uint32_t bytes = nslots * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
+    const uint32_t bytes = P.nranges * 4 * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
     mbar_arrive_expect_tx(&full[buf], bytes);
     unsigned char* base = smem + buf * STAGE_BYTES;
     const int row0 = P.next * KT;
-    for (int s = 0; s < nslots; ++s) {
-        const int b = gd->blk[s];
-        const bool isy = b >= prm.nbx;
-        tma_load_2d(base + s * SLOT_DOUBLES * 8, isy ? mapY : mapX, row0, (isy ? b - prm.nbx : b) * CB,
-                    &full[buf]);
-    }
+    tma_load_2d(base, P.isy[0] ? mapY : mapX, row0, P.col[0], &full[buf]);
+    if (P.nranges > 1)
+        tma_load_2d(base + 4 * SLOT_DOUBLES * 8, P.isy[1] ? mapY : mapX, row0, P.col[1], &full[buf]);
     if (WEIGHTED) tma_load_1d(base + MAXSLOT * SLOT_DOUBLES * 8, mapW, row0, &full[buf]);
     ++P.issued;
-    // advance the cursor
-    P.next = -1;
-    while (P.sg < P.seg_end) {
-        int st;
-        if (P.iter.next(st)) {
-            P.next = st;
-            break;
-        }
-        if (++P.sg < P.seg_end) P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
-    }
+    producer_advance(P, prm);
 }
 
 struct K1Shared {
@@ -229,27 +283,35 @@ __device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u
             }
         }
         __syncwarp();
+#ifdef JCB_K1_TRACE
+        const bool tr = prm.trace && (blockIdx.x % 45) == 0 && it < 64 && lane == 0;
+        long long* trp = prm.trace + (((int64_t)(blockIdx.x / 45) * 64 + it) * NCW + (threadIdx.x >> 5)) * 3;
+        if (tr) trp[0] = clock64();
+#endif
         mbar_wait(&sh.full[buf], ph);
+#ifdef JCB_K1_TRACE
+        if (tr) trp[1] = clock64();
+#endif
         const double* base = reinterpret_cast<const double*>(sh.smem + buf * STAGE_BYTES);
         const double* tA = base + offA;
         const double* tB = base + offB;
         const double* wt = base + MAXSLOT * SLOT_DOUBLES + 2 * kk;
         const int64_t rows_left = prm.n - (int64_t)st * KT;
-        if (!WEIGHTED && rows_left < KT) {
-            for (int k8 = 0; k8 < KT / 8; ++k8)
-                k8_step<WEIGHTED, DIAG, NBC, true>(tA + k8 * 8, tB + k8 * 8, wt + k8 * 8, pB, acc, bsum,
-                                                   wsum, sum_w, k8 * 8 + 2 * kk, (int)rows_left);
-        } else {
-#pragma unroll 1
-            for (int k8 = 0; k8 < KT / 8; ++k8) {
-                if (producer && P.next >= 0 && P.issued < it + NSTAGE &&
-                    mbar_test_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1))
-                    producer_issue<WEIGHTED>(P, prm, mapX, mapY, mapW, sh.smem, sh.full);
-                k8_step<WEIGHTED, DIAG, NBC, false>(tA + k8 * 8, tB + k8 * 8, wt + k8 * 8, pB, acc, bsum,
-                                                    wsum, sum_w, 0, KT);
-            }
-        }
+        auto poll = [&]() {
+            if (producer && P.next >= 0 && P.issued < it + NSTAGE &&
+                mbar_test_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1))
+                producer_issue<WEIGHTED>(P, prm, mapX, mapY, mapW, sh.smem, sh.full);
+        };
+        if (!WEIGHTED && rows_left < KT)
+            stage_steps<WEIGHTED, DIAG, NBC, true>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk,
+                                                   (int)rows_left, poll);
+        else
+            stage_steps<WEIGHTED, DIAG, NBC, false>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk, KT,
+                                                    poll);
         __syncwarp();
+#ifdef JCB_K1_TRACE
+        if (tr) trp[2] = clock64();
+#endif
         if (lane == 0) mbar_arrive(&sh.empty[buf]);
     }
 }
@@ -282,14 +344,8 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     P.issued = 0;
     if (producer && seg_begin < seg_end) {
         P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
-        while (P.sg < P.seg_end) {
-            int st;
-            if (P.iter.next(st)) {
-                P.next = st;
-                break;
-            }
-            if (++P.sg < P.seg_end) P.iter.init(prm.segs[P.sg], prm.nst, prm.zone_len, prm.nzones);
-        }
+        producer_load_group(P, prm);
+        producer_advance(P, prm);
         for (int s = 0; s < NSTAGE && P.next >= 0; ++s)
             producer_issue<WEIGHTED>(P, prm, &mapX, &mapY, &mapW, smem, sh.full);
     }
@@ -368,7 +424,7 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
             if (u.kind == 2) {
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
-                    double v = bsum[nb];
+                    double v = nb < 3 ? acc[3][nb][0] + acc[3][nb][1] : acc[2][0][0] + acc[2][0][1];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     if (kk == 0) out[1024 + nb * 8 + g] = v;
@@ -532,9 +588,11 @@ static int make_map_1d(CUtensorMap* map, const double* base, int64_t len, int bo
 }
 
 // Cost of a unit in DMMA pairs per k8-step, used to balance SMSPs and SMs.
-static int unit_cost(const UnitDesc& u) {
-    if (u.kind == 2) return u.nbc * (u.nbc + 1) / 2;   // upper triangle of nbc x nbc blocks
-    return 4 * u.nbc;                                  // all 4 row blocks x nbc column blocks
+// FP64-pipe cost of a unit per k8-step, in 32-cycle units (one DMMA pair = 1): DMMA pairs plus the
+// B-fragment adds (2 DADD per column block; diagonal units add 2 more for the column sums).
+static double unit_cost(const UnitDesc& u) {
+    if (u.kind == 2) return u.nbc * (u.nbc + 1) / 2 + 0.25 * u.nbc;   // upper triangle of nbc x nbc blocks
+    return 4 * u.nbc + 0.125 * u.nbc;                                 // 4 row blocks x nbc column blocks
 }
 
 struct Schedule {
@@ -564,29 +622,46 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
     auto nb8 = [&](int b) { return (blk_cols(b) + 7) / 8; };
     const int ns = (nbx + 3) / 4;
     struct RawUnit { int ba, bb, kind, sums; };
-    auto emit = [&](const std::vector<int>& slots, std::vector<RawUnit>& units) {
+    // rA, rB: up to 4 consecutive blocks each; range r occupies ring slots [4r, 4r + 4)
+    auto emit = [&](const std::vector<int>& rA, const std::vector<int>& rB, std::vector<RawUnit>& units) {
+        auto slot_of = [&](int blk) {
+            for (size_t i = 0; i < rA.size(); ++i)
+                if (rA[i] == blk) return (int)i;
+            for (size_t i = 0; i < rB.size(); ++i)
+                if (rB[i] == blk) return 4 + (int)i;
+            return -1;
+        };
         // split into groups of at most NCW units that share the slot list
         for (size_t u0 = 0; u0 < units.size(); u0 += NCW) {
             GroupDesc gd;
             memset(&gd, 0, sizeof(gd));
-            gd.nslots = (int)slots.size();
-            for (size_t s = 0; s < slots.size(); ++s) gd.blk[s] = slots[s];
+            gd.nranges = rB.empty() ? 1 : 2;
+            gd.nslots = 4 * gd.nranges;
+            for (int i = 0; i < MAXSLOT; ++i) gd.blk[i] = -1;
+            for (size_t i = 0; i < rA.size(); ++i) gd.blk[i] = rA[i];
+            for (size_t i = 0; i < rB.size(); ++i) gd.blk[4 + i] = rB[i];
+            // unused slots of a range still receive the (zero-filled or neighbouring) columns of the
+            // 128-column box; give them the block index that really lands there for bookkeeping
+            for (int r = 0; r < gd.nranges; ++r)
+                for (int i = 1; i < 4; ++i)
+                    if (gd.blk[4 * r + i] < 0) gd.blk[4 * r + i] = gd.blk[4 * r] + i;
             std::vector<UnitDesc> us;
             for (size_t k = u0; k < std::min(units.size(), u0 + NCW); ++k) {
                 UnitDesc u;
                 memset(&u, 0, sizeof(u));
-                u.sa = (int8_t)(std::find(slots.begin(), slots.end(), units[k].ba) - slots.begin());
-                u.sb = (int8_t)(std::find(slots.begin(), slots.end(), units[k].bb) - slots.begin());
+                u.sa = (int8_t)slot_of(units[k].ba);
+                u.sb = (int8_t)slot_of(units[k].bb);
                 u.kind = (int8_t)units[k].kind;
                 u.mbc = (int8_t)nb8(units[k].ba);
                 u.nbc = (int8_t)nb8(units[k].bb);
                 u.sums = (int8_t)units[k].sums;
                 us.push_back(u);
             }
-            // LPT assignment of units to warps so that the 4 SMSPs (warp % 4) carry equal DMMA load
+            // LPT assignment of units to warps so that the 4 SMSPs (warp % 4) carry equal FP64-pipe load
             std::sort(us.begin(), us.end(),
                       [](const UnitDesc& a, const UnitDesc& b) { return unit_cost(a) > unit_cost(b); });
-            int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            double load[4] = {0, 0, 0, 0};
+            int used[4] = {0, 0, 0, 0};
             for (const UnitDesc& u : us) {
                 int best = -1;
                 for (int s = 0; s < 4; ++s)
@@ -595,9 +670,9 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
                 used[best]++;
                 load[best] += unit_cost(u);
             }
-            int mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+            double mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
             S.groups.push_back(gd);
-            S.gcost.push_back((double)mx + stage_overhead());
+            S.gcost.push_back(mx + stage_overhead());
         }
     };
     bool sw_assigned = false;
@@ -606,7 +681,7 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
         for (int b = I * 4; b < std::min(nbx, I * 4 + 4); ++b) bi.push_back(b);
         // diagonal super-tile (+ X'Y and Y'Y units when they fit in the same group)
         {
-            std::vector<int> slots = bi;
+            std::vector<int> ry;
             std::vector<RawUnit> units;
             for (size_t a = 0; a < bi.size(); ++a)
                 for (size_t b = a; b < bi.size(); ++b) {
@@ -617,51 +692,47 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
                     }
                     units.push_back(u);
                 }
-            const bool merge_y = (int)bi.size() + nby <= MAXSLOT &&
+            const bool merge_y = nby <= 4 &&
                                  (int)units.size() + (int)bi.size() * nby + (I == 0 ? nby : 0) <= NCW;
             if (merge_y) {
-                for (int y = 0; y < nby; ++y) slots.push_back(nbx + y);
+                for (int y = 0; y < nby; ++y) ry.push_back(nbx + y);
                 for (int b : bi)
                     for (int y = 0; y < nby; ++y) units.push_back(RawUnit{b, nbx + y, 1, 0});
                 if (I == 0)
                     for (int y = 0; y < nby; ++y) units.push_back(RawUnit{nbx + y, nbx + y, 2, 1});
             }
-            emit(slots, units);
+            emit(bi, ry, units);
             if (!merge_y) {
                 // separate X_I' Y groups, Y blocks taken 4 at a time
                 for (int y0 = 0; y0 < nby; y0 += 4) {
-                    std::vector<int> s2 = bi;
+                    std::vector<int> s2;
                     std::vector<RawUnit> u2;
                     for (int y = y0; y < std::min(nby, y0 + 4); ++y) s2.push_back(nbx + y);
                     for (int b : bi)
                         for (int y = y0; y < std::min(nby, y0 + 4); ++y)
                             u2.push_back(RawUnit{b, nbx + y, 1, 0});
-                    emit(s2, u2);
+                    emit(bi, s2, u2);
                 }
                 if (I == 0) {
                     for (int y0 = 0; y0 < nby; y0 += MAXSLOT) {
-                        std::vector<int> s3;
+                        std::vector<int> s3, s4;
                         std::vector<RawUnit> u3;
                         for (int y = y0; y < std::min(nby, y0 + MAXSLOT); ++y) {
-                            s3.push_back(nbx + y);
+                            (y < y0 + 4 ? s3 : s4).push_back(nbx + y);
                             u3.push_back(RawUnit{nbx + y, nbx + y, 2, 1});
                         }
-                        emit(s3, u3);
+                        emit(s3, s4, u3);
                     }
                 }
             }
         }
         for (int J = I + 1; J < ns; ++J) {
-            std::vector<int> slots = bi;
             std::vector<int> bj;
-            for (int b = J * 4; b < std::min(nbx, J * 4 + 4); ++b) {
-                bj.push_back(b);
-                slots.push_back(b);
-            }
+            for (int b = J * 4; b < std::min(nbx, J * 4 + 4); ++b) bj.push_back(b);
             std::vector<RawUnit> units;
             for (int a : bi)
                 for (int b : bj) units.push_back(RawUnit{a, b, 1, 0});
-            emit(slots, units);
+            emit(bi, bj, units);
         }
     }
 }
@@ -710,6 +781,16 @@ static void build_segments(int64_t nstages, int ncta, int64_t zone_len, Schedule
     S.group_seg[ng] = cur;
     (void)nstages;
 }
+
+#ifdef JCB_K1_TRACE
+static long long* g_trace = nullptr;
+extern "C" int jcb200_debug_trace(long long* host, int n) {
+    if (!g_trace) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, g_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+    return 4 * 64 * NCW * 3;
+}
+#endif
 
 int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                  int64_t p, int64_t q, double* d_pivot) {
@@ -785,8 +866,8 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     JCB_TRY(ensure(c->partials, (size_t)nsegs * NCW * UNIT_STRIDE * 8));
 
     CUtensorMap mapX, mapY, mapW;
-    JCB_TRY(make_map_2d(&mapX, dX, n, p, ldx, KT, CB));
-    JCB_TRY(make_map_2d(&mapY, dY, n, q, ldy, KT, CB));
+    JCB_TRY(make_map_2d(&mapX, dX, n, p, ldx, KT, 4 * CB));
+    JCB_TRY(make_map_2d(&mapY, dY, n, q, ldy, KT, 4 * CB));
     if (dw) {
         JCB_TRY(make_map_1d(&mapW, dw, n, KT));
     } else {
@@ -806,6 +887,15 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     prm.q = (int)q;
     prm.nbx = nbx;
     prm.weighted = dw ? 1 : 0;
+#ifdef JCB_K1_TRACE
+    {
+        static long long* tracebuf = nullptr;
+        if (!tracebuf) cudaMalloc(&tracebuf, 4 * 64 * NCW * 3 * sizeof(long long));
+        cudaMemsetAsync(tracebuf, 0, 4 * 64 * NCW * 3 * sizeof(long long), c->stream);
+        prm.trace = tracebuf;
+        g_trace = tracebuf;
+    }
+#endif
 
     static bool attr_set = false;
     if (!attr_set) {
