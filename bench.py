@@ -198,7 +198,7 @@ def main():
     dev.fill_uniform(X, n_loc, 1, row0, n_glob)
     dev.fill_uniform(Y, n_loc, 2, row0, n_glob)
     model = dev.DeviceModel(n_loc, P, Q, NLV, device)
-    pivot = torch.empty(P + Q, dtype=torch.float64, device=device)
+    pivot = torch.empty(P + Q + 1, dtype=torch.float64, device=device)
     packed = torch.empty(dev.packed_len(P, Q), dtype=torch.float64, device=device)
 
     def step():

@@ -215,6 +215,7 @@ void jcb200_shutdown(void) {
     cudaDeviceSynchronize();
     free_buf(c->partials);
     free_buf(c->sched_dev);
+    free_buf(c->pivot_ws);
     free_buf(c->solve_ws);
     free_buf(c->xmul_ws);
     free_buf(c->hX);
@@ -378,10 +379,10 @@ int jcb200_plskern_fit_dev(double* dX, int64_t ldx, double* dY, int64_t ldy, con
     if (nlv > p) nlv = (int32_t)p;
     ARG_CHECK(nlv == 0 || (dT && dP && dR && dW && dC && dTT && ldt >= n),
               "plskern_fit_dev: NULL output");
-    JCB_TRY(ensure(c->hSmall, (size_t)(packed_len(p, q) + (p + q) + 16) * 8));
+    JCB_TRY(ensure(c->hSmall, (size_t)(packed_len(p, q) + (p + q) + 18) * 8));
     Carver cv(c->hSmall.p);
     double* d_packed = cv.take(packed_len(p, q));
-    double* d_pivot = cv.take(p + q);
+    double* d_pivot = cv.take(p + q + 1);
     double* d_sumw = cv.take(2);
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
@@ -414,7 +415,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
     JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
     JCB_TRY(ensure(c->hT, (size_t)ld * (nlv > 0 ? nlv : 1) * 8));
-    const size_t small_doubles = (size_t)packed_len(p, q) + (p + q) + 16 + 3 * (size_t)p * nlv +
+    const size_t small_doubles = (size_t)packed_len(p, q) + (p + q) + 20 + 3 * (size_t)p * nlv +
                                  (size_t)q * nlv + nlv + 2 * (p + q) + 64;
     JCB_TRY(ensure(c->hSmall, small_doubles * 8));
     double* dX = (double*)c->hX.p;
@@ -424,7 +425,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     double* dT = (double*)c->hT.p;
     Carver cv(c->hSmall.p);
     double* d_packed = cv.take(packed_len(p, q));
-    double* d_pivot = cv.take(p + q);
+    double* d_pivot = cv.take(p + q + 1);
     double* d_sumw = cv.take(2);
     double* dP = cv.take((size_t)p * nlv);
     double* dR = cv.take((size_t)p * nlv);

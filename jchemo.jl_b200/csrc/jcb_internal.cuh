@@ -64,6 +64,7 @@ struct Ctx {
     int64_t sk_zone_len = 0;
     size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
+    Buf pivot_ws;
     Buf solve_ws;
     Buf xmul_ws;
     // general scratch for the host-pointer API

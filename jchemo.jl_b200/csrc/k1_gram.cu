@@ -125,7 +125,7 @@ struct GramParams {
 // Within a group all first k-halves are issued before any second half, so the two dependent DMMAs of
 // an accumulator are >= 8 (full) or >= 10 (diagonal) issue slots apart.
 // (A register-level software pipeline of the B transform was tried and was slower: 128 registers.)
-template <bool WEIGHTED, bool DIAG, int NBC, bool MASKED, typename Poll>
+template <bool WEIGHTED, bool DIAG, int NBC, bool CENTER, bool MASKED, typename Poll>
 __device__ __forceinline__ void stage_steps(const double* __restrict__ tA, const double* __restrict__ tB,
                                             const double* __restrict__ wt, const double (&pB)[4],
                                             double (&acc)[4][4][2], double (&bsum)[4], double& wsum,
@@ -156,12 +156,13 @@ __device__ __forceinline__ void stage_steps(const double* __restrict__ tA, const
                 const int nb = n0 + j;
                 if (nb < NBC) {
                     b[j] = *reinterpret_cast<const double2*>(tB + k8 * 8 + nb * 8 * KT);
-                    if (WEIGHTED || MASKED) {
-                        b[j].x = (b[j].x - pB[nb]) * w2.x;
-                        b[j].y = (b[j].y - pB[nb]) * w2.y;
-                    } else {
+                    if (CENTER) {
                         b[j].x -= pB[nb];
                         b[j].y -= pB[nb];
+                    }
+                    if (WEIGHTED || MASKED) {
+                        b[j].x *= w2.x;
+                        b[j].y *= w2.y;
                     }
                     if (DIAG) {
                         // column sums ride in the accumulator blocks below the diagonal, which a
@@ -259,7 +260,7 @@ struct K1Shared {
 // All stages of one segment for one warp-unit variant: a tight loop with the variant dispatch hoisted
 // out (the per-stage bookkeeping is on the critical path: at a stage boundary the four warps of an
 // SMSP leave the DMMA pipe idle together).
-template <bool WEIGHTED, bool DIAG, int NBC>
+template <bool WEIGHTED, bool DIAG, int NBC, bool CENTER>
 __device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u, const GramParams& prm,
                                             const CUtensorMap* mapX, const CUtensorMap* mapY,
                                             const CUtensorMap* mapW, const K1Shared sh, Producer& P,
@@ -302,12 +303,14 @@ __device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u
                 mbar_test_wait(&sh.empty[P.issued % NSTAGE], ((P.issued / NSTAGE) & 1) ^ 1))
                 producer_issue<WEIGHTED>(P, prm, mapX, mapY, mapW, sh.smem, sh.full);
         };
-        if (!WEIGHTED && rows_left < KT)
-            stage_steps<WEIGHTED, DIAG, NBC, true>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk,
-                                                   (int)rows_left, poll);
+        // tail stage of the unweighted kernel: zero-filled rows must get weight 0 when they are centred
+        // (0 - c != 0) or counted (sum of weights); without centring they contribute nothing anyway
+        if (!WEIGHTED && rows_left < KT && (CENTER || (DIAG && sum_w)))
+            stage_steps<WEIGHTED, DIAG, NBC, CENTER, true>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk,
+                                                           (int)rows_left, poll);
         else
-            stage_steps<WEIGHTED, DIAG, NBC, false>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk, KT,
-                                                    poll);
+            stage_steps<WEIGHTED, DIAG, NBC, CENTER, false>(tA, tB, wt, pB, acc, bsum, wsum, sum_w,
+                                                            2 * kk, KT, poll);
         __syncwarp();
 #ifdef JCB_K1_TRACE
         if (tr) trp[2] = clock64();
@@ -351,6 +354,9 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     }
 
     const int g = lane >> 2, kk = lane & 3;
+    // pivot[p + q] != 0: the columns are centred about the pivot inside the loop; == 0: the pivot is all
+    // zeros (well-scaled columns, decided by the pivot kernel) and the loop is pure LDS + DMMA
+    const bool center = prm.pivot[prm.p + prm.q] != 0.0;
     uint32_t it = 0;  // stages consumed by this CTA so far (ring position)
     for (int sg = seg_begin; sg < seg_end; ++sg) {
         const SegDesc seg = prm.segs[sg];
@@ -380,9 +386,15 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
                 }
             }
         }
-#define JCB_SEG(D, N)                                                                                  \
-    run_segment<WEIGHTED, D, N>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, g, kk, pB, acc, \
-                                bsum, wsum)
+#define JCB_SEG(D, N)                                                                                \
+    do {                                                                                             \
+        if (center)                                                                                  \
+            run_segment<WEIGHTED, D, N, true>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, g, \
+                                              kk, pB, acc, bsum, wsum);                              \
+        else                                                                                         \
+            run_segment<WEIGHTED, D, N, false>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, \
+                                               g, kk, pB, acc, bsum, wsum);                          \
+    } while (0)
         switch (u.kind ? ((u.kind == 2 ? 4 : 0) + (u.nbc - 1)) : -1) {
             case 0: JCB_SEG(false, 1); break;
             case 1: JCB_SEG(false, 2); break;
@@ -498,32 +510,71 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
 // Strided-sample pivot: mean of up to 65536 rows per column, taken as 256 evenly spaced chunks of 256
 // consecutive rows (coalesced 2 KB reads).  One block per column.  The pivot only has to be CLOSE to
 // the mean (K3 corrects exactly); a large sample keeps the correction terms c_i s_j and delta delta'
-// far below the rounding level even for offset-heavy data.
+// far below the rounding level even for offset-heavy data.  ratio[col] = mean^2 / variance of the
+// sample tells how much centring matters for this column.
 __global__ void __launch_bounds__(256)
 pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-             int64_t n, int p, int q, double* __restrict__ pivot) {
+             int64_t n, int p, int q, double* __restrict__ pivot, double* __restrict__ ratio) {
     const int col = blockIdx.x;
     const double* src = col < p ? X + (int64_t)col * ldx : Y + (int64_t)(col - p) * ldy;
-    __shared__ double red[8];
-    double s = 0.0;
+    __shared__ double red[16];
+    double s = 0.0, s2 = 0.0;
     int64_t cnt;
     if (n <= 65536) {
         cnt = n;
-        for (int64_t i = threadIdx.x; i < n; i += 256) s += src[i];
+        for (int64_t i = threadIdx.x; i < n; i += 256) {
+            const double v = src[i];
+            s += v;
+            s2 += v * v;
+        }
     } else {
         cnt = 65536;
         const int64_t stride = n / 256;            // chunk c covers rows [c*stride, c*stride + 256)
-        for (int c = 0; c < 256; ++c) s += src[c * stride + threadIdx.x];
+        for (int c = 0; c < 256; ++c) {
+            const double v = src[c * stride + threadIdx.x];
+            s += v;
+            s2 += v * v;
+        }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = s;
+        red[8 + (threadIdx.x >> 5)] = s2;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        pivot[col] = t / (double)cnt;
+        double t = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            t += red[w];
+            t2 += red[8 + w];
+        }
+        const double m = t / (double)cnt;
+        const double var = t2 / (double)cnt - m * m;
+        pivot[col] = m;
+        // a (near-)constant column has no usable variance estimate: always centre
+        ratio[col] = (var > 1e-12 * (m * m) && var > 0.0) ? (m * m) / var : 1e300;
     }
+}
+
+// Centring costs FP64-pipe cycles that the DMMAs need.  When every column has mean^2 <= 64 variance,
+// second moments about 0 lose at most ~2 digits to the mean (K3 removes it exactly: pivot = 0 is just
+// another pivot), far inside the 1e-10 budget, so the pivot is zeroed and K1 runs without centring.
+// pivot[p + q] = 1 (centring on) or 0 (pivot all zeros).  JCB_FORCE_CENTER=1 keeps centring on.
+__global__ void pivot_decide_kernel(double* __restrict__ pivot, const double* __restrict__ ratio,
+                                    int ncol, int force_center) {
+    __shared__ int need;
+    if (threadIdx.x == 0) need = force_center;
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x)
+        if (!(ratio[c] <= 64.0)) need = 1;
+    __syncthreads();
+    if (!need)
+        for (int c = threadIdx.x; c < ncol; c += blockDim.x) pivot[c] = 0.0;
+    if (threadIdx.x == 0) pivot[ncol] = need ? 1.0 : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -794,7 +845,20 @@ extern "C" int jcb200_debug_trace(long long* host, int n) {
 
 int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                  int64_t p, int64_t q, double* d_pivot) {
-    pivot_kernel<<<(int)(p + q), 256, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot);
+    JCB_TRY(ensure(c->pivot_ws, (size_t)(p + q) * 8));
+    // Measured on B200 (profiles/k1_r01_notes.md): the centring-free loop is NOT faster (8.65 vs 8.45 ms
+    // at C2 — the loop is bound by LDS -> DMMA issue latency, not by the 8 DADDs per k8-step), so
+    // centring stays on unless JCB_AUTO_NOCENTER=1 asks for the data-dependent decision.
+    static int force = -1;
+    if (force < 0) {
+        const char* e = getenv("JCB_AUTO_NOCENTER");
+        force = (e && atoi(e)) ? 0 : 1;
+    }
+    pivot_kernel<<<(int)(p + q), 256, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot,
+                                                      (double*)c->pivot_ws.p);
+    JCB_LAUNCH_CHECK();
+    pivot_decide_kernel<<<1, 256, 0, c->stream>>>(d_pivot, (const double*)c->pivot_ws.p, (int)(p + q),
+                                                  force);
     JCB_LAUNCH_CHECK();
     return 0;
 }

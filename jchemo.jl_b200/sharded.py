@@ -41,7 +41,7 @@ def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, pac
     """X [p, ld], Y [q, ld], w [n_local] or None hold this rank's rows on its GPU."""
     p, q = X.shape[0], Y.shape[0]
     if pivot is None:
-        pivot = torch.empty(p + q, dtype=torch.float64, device=X.device)
+        pivot = torch.empty(p + q + 1, dtype=torch.float64, device=X.device)
     if packed is None:
         packed = torch.empty(dev.packed_len(p, q), dtype=torch.float64, device=X.device)
     dev.pivot_dev(X, Y, n_local, pivot)
