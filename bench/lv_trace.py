@@ -1,0 +1,21 @@
+"""Debug: per-phase clock64 totals of the LV loop (needs a -DJCB_K1_TRACE build selected with JCB_LIB)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from jchemo_b200 import device as dev, sharded
+n, p, q, nlv = 200_000, int(os.environ.get("P", 500)), int(os.environ.get("Q", 10)), int(os.environ.get("NLV", 25))
+torch.cuda.set_device(0); dev.init(0); dev.use_current_stream()
+X = dev.colmajor_empty(n, p); Y = dev.colmajor_empty(n, q)
+dev.fill_uniform(X, n, 1); dev.fill_uniform(Y, n, 2)
+model = dev.DeviceModel(n, p, q, nlv)
+for _ in range(2):
+    sharded.fit_sharded(X, Y, None, n, model)
+torch.cuda.synchronize()
+raw = C.CDLL(os.environ["JCB_LIB"])
+buf = (C.c_longlong * 16)()
+raw.jcb200_debug_lv_trace(buf)
+names = ["M=XtY'XtY", "eig squaring", "v refine", "w=XtY v", "dots+r", "zp matvec + u", "cluster.sync", "tt,c", "deflate+store", "loop top"]
+tot = sum(buf[i] for i in range(10))
+for i, nm in enumerate(names):
+    print(f"{nm:16s} {buf[i]:10d} cyc  {buf[i]/1965e3:8.3f} ms  {100*buf[i]/max(tot,1):5.1f}%")
+print("total", tot/1965e3, "ms")

@@ -106,6 +106,102 @@ __device__ double block_sum(double v, double* red) {
     return t;
 }
 
+// Dominant eigenvector of the symmetric PSD Q x Q matrix M by repeated squaring, ONE warp, compile-time Q
+// (all loops unrolled, no integer division, no block barrier).  L = 32/Q lanes share row i; a lane owns
+// the entries (i, jl + u*L).  A <- A*A (A symmetric: column j = row j, both operands contiguous rows)
+// converges quadratically to a multiple of v v'.  The matrix is renormalised by its trace every third
+// squaring, where convergence is checked: if the normalised matrix moved by < 1e-4 over the last three
+// squarings, the contamination three squarings ago was <~ 1e-4 and is now its 8th power.
+// Result: column `best` (largest diagonal) of the converged matrix in v_out[0..Q).
+template <int Q>
+__device__ __forceinline__ void eig_dominant_warp(const double* __restrict__ M_s, double* __restrict__ bufA,
+                                                  double* __restrict__ bufB, double* __restrict__ v_out,
+                                                  const int lane) {
+    constexpr int L = 32 / Q;
+    constexpr int NJ = (Q + L - 1) / L;
+    const int i = lane / L, jl = lane - i * L;
+    const bool act = i < Q;
+    double tr = 0.0;
+#pragma unroll
+    for (int d = 0; d < Q; ++d) tr += M_s[d * Q + d];
+    const double itr = 1.0 / tr;
+    double prev[NJ];
+    double* cur = bufA;
+    double* nxt = bufB;
+#pragma unroll
+    for (int u = 0; u < NJ; ++u) {
+        const int j = jl + u * L;
+        prev[u] = 0.0;
+        if (act && j < Q) {
+            prev[u] = M_s[i * Q + j] * itr;
+            cur[i * Q + j] = prev[u];
+        }
+    }
+    __syncwarp();
+    for (int iter = 0; iter < 90; ++iter) {
+        double acc[NJ];
+#pragma unroll
+        for (int u = 0; u < NJ; ++u) acc[u] = 0.0;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                const double aik = cur[i * Q + k];
+#pragma unroll
+                for (int u = 0; u < NJ; ++u) {
+                    const int j = jl + u * L;
+                    if (j < Q) acc[u] += aik * cur[j * Q + k];
+                }
+            }
+        }
+        if (iter % 3 != 2) {
+            if (act) {
+#pragma unroll
+                for (int u = 0; u < NJ; ++u) {
+                    const int j = jl + u * L;
+                    if (j < Q) nxt[i * Q + j] = acc[u];
+                }
+            }
+            __syncwarp();
+        } else {
+            // trace of the new matrix = sum of its diagonal entries: collect them through a shuffle sum
+            double dg = 0.0;
+#pragma unroll
+            for (int u = 0; u < NJ; ++u) {
+                const int j = jl + u * L;
+                if (act && j == i) dg = acc[u];
+            }
+            const double inv = 1.0 / warp_sum(dg);
+            double chg = 0.0;
+#pragma unroll
+            for (int u = 0; u < NJ; ++u) {
+                const int j = jl + u * L;
+                if (act && j < Q) {
+                    const double nv = acc[u] * inv;
+                    chg = fmax(chg, fabs(nv - prev[u]));
+                    prev[u] = nv;
+                    nxt[i * Q + j] = nv;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) chg = fmax(chg, __shfl_xor_sync(0xffffffffu, chg, o));
+            __syncwarp();
+            if (chg < 1e-4) {
+                cur = nxt;
+                break;
+            }
+        }
+        double* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    __syncwarp();
+    int best = 0;
+#pragma unroll
+    for (int d = 1; d < Q; ++d)
+        if (cur[d * Q + d] > cur[best * Q + best]) best = d;
+    if (lane < Q) v_out[lane] = cur[lane * Q + best];
+}
+
 struct LvParams {
     const double* XtX;   // p x p, symmetric, read only
     double* XtY;         // p x q (K3 output); deflated in place only when it does not fit in smem
@@ -119,7 +215,23 @@ struct LvParams {
     int xty_smem;        // XtY resident in shared memory (every CTA deflates its own full copy)
     double* Ppriv;       // LV_CLUSTER private copies of P and R (p x nlv each): with XtY in smem a CTA
     double* Rpriv;       // reads back only what it wrote itself, so one cluster barrier per LV suffices
+#ifdef JCB_K1_TRACE
+    long long* trace;    // debug builds: accumulated clock64 per phase (CTA 0, thread 0)
+#endif
 };
+
+#ifdef JCB_K1_TRACE
+#define LV_MARK(idx)                                                        \
+    do {                                                                    \
+        if (rank == 0 && tid == 0 && prm.trace) {                           \
+            const long long _t = clock64();                                 \
+            prm.trace[idx] += _t - tmark;                                   \
+            tmark = _t;                                                     \
+        }                                                                   \
+    } while (0)
+#else
+#define LV_MARK(idx) do { } while (0)
+#endif
 
 // dot of a shared vector with a global column, lanes strided, 8 independent loads in flight
 __device__ __forceinline__ double warp_dot_gs(const double* __restrict__ gcol,
@@ -162,7 +274,8 @@ lvloop_kernel(const LvParams prm) {
     double* A_s = zp_s + p;       // q*q
     double* B_s = A_s + q * q;    // q*q
     double* M_s = B_s + q * q;    // q*q
-    double* v_s = M_s + q * q;    // q
+    double* N_s = M_s + q * q;    // q*q
+    double* v_s = N_s + q * q;    // q
     double* c_s = v_s + q;        // q
     double* d_s = c_s + q;        // nlv (dots w'P_j)
     double* red = d_s + nlv;      // 64
@@ -182,7 +295,11 @@ lvloop_kernel(const LvParams prm) {
         __syncthreads();
     }
 
+#ifdef JCB_K1_TRACE
+    long long tmark = clock64();
+#endif
     for (int a = 0; a < nlv; ++a) {
+        LV_MARK(9);
         // ---------------------------------------------------------------- (1) weight vector w
         if (q == 1) {
             double s = 0.0;
@@ -194,111 +311,137 @@ lvloop_kernel(const LvParams prm) {
             const double nrm = sqrt(block_sum(s, red));
             for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
         } else {
-            // M = XtY' XtY (symmetric q x q): one warp per (i <= j) pair
+            // M = XtY' XtY (symmetric q x q): a warp takes up to 4 (i <= j) pairs per pass so that their
+            // loads and reductions overlap
             const int npair = q * (q + 1) / 2;
-            for (int pr = warp; pr < npair; pr += nwarp) {
-                int i = 0, rem = pr;
-                while (rem >= q - i) { rem -= q - i; ++i; }
-                const int j = i + rem;
-                double s;
-                if (xs) {
-                    s = warp_dot_ss(xty_s + (int64_t)i * P64, xty_s + (int64_t)j * P64, p, lane);
-                } else {
-                    const double* ci = prm.XtY + (int64_t)i * P64;
-                    const double* cj = prm.XtY + (int64_t)j * P64;
-                    double s0 = 0.0, s1 = 0.0;
-                    int k = lane;
-                    for (; k + 32 < p; k += 64) {
-                        const double a0 = __ldcg(ci + k), b0 = __ldcg(cj + k);
-                        const double a1 = __ldcg(ci + k + 32), b1 = __ldcg(cj + k + 32);
-                        s0 += a0 * b0;
-                        s1 += a1 * b1;
-                    }
-                    if (k < p) s0 += __ldcg(ci + k) * __ldcg(cj + k);
-                    s = warp_sum(s0 + s1);
+            for (int pr0 = warp; pr0 < npair; pr0 += 4 * nwarp) {
+                int pi[4], pj[4];
+                double acc4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int pr = min(pr0 + u * nwarp, npair - 1);
+                    int i = 0, rem = pr;
+                    while (rem >= q - i) { rem -= q - i; ++i; }
+                    pi[u] = i;
+                    pj[u] = i + rem;
+                    acc4[u] = 0.0;
                 }
-                if (lane == 0) { M_s[i * q + j] = s; M_s[j * q + i] = s; }
+                if (xs) {
+                    const double* c0 = xty_s + pi[0] * p; const double* d0 = xty_s + pj[0] * p;
+                    const double* c1 = xty_s + pi[1] * p; const double* d1 = xty_s + pj[1] * p;
+                    const double* c2 = xty_s + pi[2] * p; const double* d2 = xty_s + pj[2] * p;
+                    const double* c3 = xty_s + pi[3] * p; const double* d3 = xty_s + pj[3] * p;
+#pragma unroll 4
+                    for (int k = lane; k < p; k += 32) {
+                        acc4[0] += c0[k] * d0[k];
+                        acc4[1] += c1[k] * d1[k];
+                        acc4[2] += c2[k] * d2[k];
+                        acc4[3] += c3[k] * d3[k];
+                    }
+                } else {
+                    for (int k = lane; k < p; k += 32) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            acc4[u] += __ldcg(prm.XtY + k + (int64_t)pi[u] * P64) *
+                                       __ldcg(prm.XtY + k + (int64_t)pj[u] * P64);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc4[u] += __shfl_xor_sync(0xffffffffu, acc4[u], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (pr0 + u * nwarp < npair) {
+                            M_s[pi[u] * q + pj[u]] = acc4[u];
+                            M_s[pj[u] * q + pi[u]] = acc4[u];
+                        }
+                    }
+                }
             }
             __syncthreads();
-            // dominant eigenvector by repeated squaring of the trace-normalised matrix:
-            // A <- A*A / tr(A*A) converges quadratically to v v' (tr(A*A) = ||A||_F^2, A symmetric).
-            // One thread per entry, two named barriers per squaring among the warps that hold entries.
-            // Once the largest change drops below 1e-12 the contamination is below 1e-24 one squaring
-            // later; two more are done for margin.
-            {
+            LV_MARK(0);
+            if (q <= 16) {
+                if (warp == 0) {
+                    switch (q) {
+#define JCB_EIG(Q) case Q: eig_dominant_warp<Q>(M_s, A_s, B_s, v_s, lane); break;
+                        JCB_EIG(2) JCB_EIG(3) JCB_EIG(4) JCB_EIG(5) JCB_EIG(6) JCB_EIG(7) JCB_EIG(8)
+                        JCB_EIG(9) JCB_EIG(10) JCB_EIG(11) JCB_EIG(12) JCB_EIG(13) JCB_EIG(14)
+                        JCB_EIG(15) JCB_EIG(16)
+#undef JCB_EIG
+                        default: break;
+                    }
+                }
+                __syncthreads();
+            } else {
+                // generic q: one thread per entry, ping-pong buffers, one named barrier per squaring,
+                // trace renormalisation + convergence check every third squaring (as above)
                 const int qq = q * q;
                 const int ew = min(nwarp, (qq + 31) / 32);          // warps that take part
                 const int eth = ew * 32;
                 if (warp < ew) {
                     double tr = 0.0;
                     for (int i = 0; i < q; ++i) tr += M_s[i * q + i];
-                    for (int e = tid; e < qq; e += eth) A_s[e] = M_s[e] / tr;
+                    double* cur = A_s;
+                    double* nxt = B_s;
+                    for (int e = tid; e < qq; e += eth) {
+                        cur[e] = M_s[e] / tr;
+                        N_s[e] = cur[e];            // last normalised state, for the convergence check
+                    }
                     asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
-                    int extra = 0;
-                    for (int iter = 0; iter < 80; ++iter) {
-                        double sq = 0.0;
+                    for (int iter = 0; iter < 90; ++iter) {
                         for (int e = tid; e < qq; e += eth) {
                             const int i = e / q, j = e - i * q;
-                            const double* ai = A_s + i * q;
-                            const double* aj = A_s + j;
+                            const double* ai = cur + i * q;
+                            const double* aj = cur + j * q;
                             double s0 = 0.0, s1 = 0.0;
                             int k = 0;
                             for (; k + 1 < q; k += 2) {
-                                s0 += ai[k] * aj[k * q];
-                                s1 += ai[k + 1] * aj[(k + 1) * q];
+                                s0 += ai[k] * aj[k];
+                                s1 += ai[k + 1] * aj[k + 1];
                             }
-                            if (k < q) s0 += ai[k] * aj[k * q];
-                            B_s[e] = s0 + s1;
-                            const double aij = ai[j];
-                            sq += aij * aij;
+                            if (k < q) s0 += ai[k] * aj[k];
+                            nxt[e] = s0 + s1;
                         }
-                        sq = warp_sum(sq);
-                        if (lane == 0) red[warp] = sq;
                         asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
-                        double t2 = 0.0;
-                        for (int w2 = 0; w2 < ew; ++w2) t2 += red[w2];
-                        double chg = 0.0;
-                        for (int e = tid; e < qq; e += eth) {
-                            const double nv = B_s[e] / t2;
-                            chg = fmax(chg, fabs(nv - A_s[e]));
-                            A_s[e] = nv;
-                        }
+                        double* t = cur; cur = nxt; nxt = t;
+                        if (iter % 3 == 2) {
+                            double t2 = 0.0;
+                            for (int d = 0; d < q; ++d) t2 += cur[d * q + d];
+                            double chg = 0.0;
+                            for (int e = tid; e < qq; e += eth) {
+                                const double nv = cur[e] / t2;
+                                chg = fmax(chg, fabs(nv - N_s[e]));
+                                nxt[e] = nv;
+                            }
 #pragma unroll
-                        for (int o = 16; o; o >>= 1) chg = fmax(chg, __shfl_xor_sync(0xffffffffu, chg, o));
-                        if (lane == 0) red[32 + warp] = chg;
+                            for (int o = 16; o; o >>= 1)
+                                chg = fmax(chg, __shfl_xor_sync(0xffffffffu, chg, o));
+                            if (lane == 0) red[32 + warp] = chg;
+                            asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
+                            t = cur; cur = nxt; nxt = t;
+                            double cmax = 0.0;
+                            for (int w2 = 0; w2 < ew; ++w2) cmax = fmax(cmax, red[32 + w2]);
+                            if (cmax < 1e-4) break;
+                            for (int e = tid; e < qq; e += eth) N_s[e] = cur[e];   // own entries only
+                        }
+                    }
+                    // v = column with the largest diagonal entry of the converged matrix
+                    if (warp == 0) {
                         asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
-                        double cmax = 0.0;
-                        for (int w2 = 0; w2 < ew; ++w2) cmax = fmax(cmax, red[32 + w2]);
-                        if (cmax < 1e-12 && ++extra == 3) break;
+                        int best = 0;
+                        for (int i = 1; i < q; ++i) if (cur[i * q + i] > cur[best * q + best]) best = i;
+                        for (int i = lane; i < q; i += 32) v_s[i] = cur[i * q + best];
+                    } else {
+                        asm volatile("bar.sync 1, %0;" ::"r"(eth) : "memory");
                     }
                 }
                 __syncthreads();
             }
-            // v = column with the largest diagonal entry, then two refining power steps on M
-            if (warp == 0) {
-                int best = 0;
-                for (int i = 1; i < q; ++i) if (A_s[i * q + i] > A_s[best * q + best]) best = i;
-                for (int i = lane; i < q; i += 32) v_s[i] = A_s[i * q + best];
-                __syncwarp();
-                for (int rep = 0; rep < 3; ++rep) {
-                    double s = 0.0;
-                    for (int i = lane; i < q; i += 32) s += v_s[i] * v_s[i];
-                    s = sqrt(warp_sum(s));
-                    __syncwarp();
-                    for (int i = lane; i < q; i += 32) v_s[i] /= s;
-                    __syncwarp();
-                    if (rep == 2) break;
-                    for (int i = lane; i < q; i += 32) {
-                        double t = 0.0;
-                        for (int k = 0; k < q; ++k) t += M_s[i * q + k] * v_s[k];
-                        c_s[i] = t;
-                    }
-                    __syncwarp();
-                    for (int i = lane; i < q; i += 32) v_s[i] = c_s[i];
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
+            LV_MARK(1);
+            LV_MARK(2);
             // w = XtY v / ||.||
             double s = 0.0;
             for (int k = tid; k < p; k += LV_THREADS) {
@@ -315,6 +458,7 @@ lvloop_kernel(const LvParams prm) {
             for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
         }
         __syncthreads();
+        LV_MARK(3);
         // ---------------------------------------------------------------- (2) r
         for (int j = warp; j < a; j += nwarp) {
             const double s = warp_dot_gs(Pr + (int64_t)j * P64, w_s, p, lane);
@@ -335,24 +479,43 @@ lvloop_kernel(const LvParams prm) {
             r_s[k] = rv;
         }
         __syncthreads();
+        LV_MARK(4);
         // ---------------------------------------------------------------- (3) zp slice = XtX[lo:hi, :] r
         double* zp_g = prm.zp + (a & 1) * P64;
-        for (int i = lo + warp; i < hi; i += nwarp) {
+        for (int i = lo + warp; i < hi; i += 2 * nwarp) {
+            // two rows per pass: 16 independent L2 loads in flight per lane
+            const int i2 = i + nwarp;
+            const bool two = i2 < hi;
             const double* row = prm.XtX + (int64_t)i * P64;   // symmetric: row i == column i
-            double s[8];
+            const double* row2 = prm.XtX + (int64_t)(two ? i2 : i) * P64;
+            double s[8], t[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s[u] = 0.0;
+            for (int u = 0; u < 8; ++u) s[u] = t[u] = 0.0;
             int k = lane;
             for (; k + 7 * 32 < p; k += 8 * 32) {
-                double v[8];
+                double v[8], v2[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = row[k + u * 32];
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = row[k + u * 32];
+                    v2[u] = row2[k + u * 32];
+                }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s[u] += v[u] * r_s[k + u * 32];
+                for (int u = 0; u < 8; ++u) {
+                    const double rk = r_s[k + u * 32];
+                    s[u] += v[u] * rk;
+                    t[u] += v2[u] * rk;
+                }
             }
-            for (; k < p; k += 32) s[0] += row[k] * r_s[k];
-            const double t = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
-            if (lane == 0) __stcg(zp_g + i, t);
+            for (; k < p; k += 32) {
+                s[0] += row[k] * r_s[k];
+                t[0] += row2[k] * r_s[k];
+            }
+            const double z1 = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+            const double z2 = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
+            if (lane == 0) {
+                __stcg(zp_g + i, z1);
+                if (two) __stcg(zp_g + i2, z2);
+            }
         }
         // u = XtY' r (pre-deflation XtY; c = u / tt once tt is known)
         for (int j = warp; j < q; j += nwarp) {
@@ -361,8 +524,10 @@ lvloop_kernel(const LvParams prm) {
             else t = warp_dot_gs(prm.XtY + (int64_t)j * P64, r_s, p, lane);
             if (lane == 0) c_s[j] = t;
         }
+        LV_MARK(5);
         // barrier 1: zp slices visible; every CTA has finished reading the pre-deflation XtY
         cluster.sync();
+        LV_MARK(6);
         // ---------------------------------------------------------------- (4) tt, c
         double s = 0.0;
         for (int k = tid; k < p; k += LV_THREADS) {
@@ -374,6 +539,7 @@ lvloop_kernel(const LvParams prm) {
         __syncthreads();
         for (int j = tid; j < q; j += LV_THREADS) c_s[j] /= tt;
         __syncthreads();
+        LV_MARK(7);
         // ---------------------------------------------------------------- (5) deflate, store
         if (xs) {
             // every CTA deflates its own full shared copy (bit-identical everywhere)
@@ -414,6 +580,16 @@ lvloop_kernel(const LvParams prm) {
     }
 }
 
+#ifdef JCB_K1_TRACE
+static long long* g_lv_trace = nullptr;
+extern "C" int jcb200_debug_lv_trace(long long* host) {
+    if (!g_lv_trace) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, g_lv_trace, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return 16;
+}
+#endif
+
 int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
                  int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
                  double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
@@ -453,7 +629,16 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
     prm.nlv = nlv;
     prm.Ppriv = Ppriv;
     prm.Rpriv = Rpriv;
-    size_t smem = (size_t)(3 * p + 3 * q * q + 2 * q + nlv + 64) * 8;
+#ifdef JCB_K1_TRACE
+    {
+        static long long* tb = nullptr;
+        if (!tb) cudaMalloc(&tb, 16 * sizeof(long long));
+        cudaMemsetAsync(tb, 0, 16 * sizeof(long long), c->stream);
+        prm.trace = tb;
+        g_lv_trace = tb;
+    }
+#endif
+    size_t smem = (size_t)(3 * p + 4 * q * q + 2 * q + nlv + 64) * 8;
     prm.xty_smem = (smem + (size_t)p * q * 8 <= 160 * 1024) ? 1 : 0;
     if (prm.xty_smem) smem += (size_t)p * q * 8;
     if (smem > 200 * 1024) {

@@ -1,0 +1,168 @@
+"""
+    JchemoB200
+
+Drop-in for the kernel-PLS path of Jchemo.jl (`plskern`, `plskern!`, `transform`, `coef`, `predict` on
+`Plsr`; reference: `src/plskern.jl:1-238`).  Same function names, argument meaning, returned fields and
+field order; the arithmetic runs on an NVIDIA B200 in `libjchemo_b200.so` (hand-written sm_100a CUDA)
+through the C ABI declared in `include/jchemo_b200.h`.  There is no CPU fallback: without the library
+or a B200 every call raises.
+
+The library path is taken from `ENV["JCHEMO_B200_LIB"]`, else `libjchemo_b200.so` next to this package.
+
+NOTE: this file could not be executed in the build container (no Julia toolchain there); the same ABI
+is exercised end to end by the Python ctypes mirror in `jchemo.jl_b200/plskern.py` and `tests/`.
+"""
+module JchemoB200
+
+using LinearAlgebra
+using Libdl
+
+export Plsr, plskern, plskern!, transform, coef, predict
+
+const LIB = get(ENV, "JCHEMO_B200_LIB",
+                normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
+
+# ---------------------------------------------------------------- struct (src/plskern.jl:1-14)
+struct Plsr
+    T::Matrix{Float64}
+    P::Matrix{Float64}
+    R::Matrix{Float64}
+    W::Matrix{Float64}
+    C::Matrix{Float64}
+    TT::Vector{Float64}
+    xmeans::Vector{Float64}
+    xscales::Vector{Float64}
+    ymeans::Vector{Float64}
+    yscales::Vector{Float64}
+    weights::Vector{Float64}
+    niter::Union{Array{Float64}, Nothing}
+end
+
+# `V` is the north-star spelling of the X-loadings `P`
+Base.getproperty(o::Plsr, s::Symbol) = s === :V ? getfield(o, :P) : getfield(o, s)
+Base.propertynames(::Plsr) = (fieldnames(Plsr)..., :V)
+
+# ---------------------------------------------------------------- helpers (src/utility.jl)
+ensure_mat(X::AbstractMatrix) = X                                   # utility.jl:544
+ensure_mat(X::AbstractVector) = Matrix(reshape(X, :, 1))            # :545
+ensure_mat(X::Number) = reshape([X], 1, 1)                          # :546
+ensure_mat(X::LinearAlgebra.Adjoint) = Matrix(X)                    # :547
+ensure_mat(X) = Matrix(X)                                           # DataFrame etc. (:548)
+nro(X) = size(X, 1)
+nco(X) = size(X, 2)
+
+dense64(X) = X isa Matrix{Float64} ? X : Matrix{Float64}(X)
+
+function check(rc::Cint, what::AbstractString)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:jcb200_last_error, LIB), Cstring, ()))
+    error("JchemoB200.$what failed (status $rc): $msg")
+end
+
+# ---------------------------------------------------------------- fit (src/plskern.jl:106-178)
+function _fit(X::Matrix{Float64}, Y::Matrix{Float64}, weights, nlv::Integer, scal::Bool, writeback::Bool)
+    n, p = size(X)
+    q = nco(Y)
+    nro(Y) == n || throw(DimensionMismatch("X has $n rows, Y has $(nro(Y))"))
+    a = max(0, min(n, p, nlv))                                      # :116
+    w = weights === nothing ? nothing : Vector{Float64}(vec(weights))
+    w === nothing || length(w) == n || throw(DimensionMismatch("weights has length $(length(w))"))
+    T = Matrix{Float64}(undef, n, a); P = Matrix{Float64}(undef, p, a)
+    R = Matrix{Float64}(undef, p, a); W = Matrix{Float64}(undef, p, a)
+    C = Matrix{Float64}(undef, q, a); TT = Vector{Float64}(undef, a)
+    xmeans = Vector{Float64}(undef, p); xscales = Vector{Float64}(undef, p)
+    ymeans = Vector{Float64}(undef, q); yscales = Vector{Float64}(undef, q)
+    wout = Vector{Float64}(undef, n)
+    nlv_out = Ref{Int32}(0)
+    rc = ccall((:jcb200_plskern_fit, LIB), Cint,
+               (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int32, Int32,
+                Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ref{Int32}),
+               X, max(n, 1), Y, max(n, 1), w === nothing ? C_NULL : w, n, p, q, nlv, scal, writeback,
+               T, max(n, 1), P, R, W, C, TT, xmeans, xscales, ymeans, yscales, wout, nlv_out)
+    check(rc, "plskern")
+    Plsr(T, P, R, W, C, TT, xmeans, xscales, ymeans, yscales, wout, nothing)
+end
+
+"""
+    plskern(X, Y, weights = ones(nro(X)); nlv, scal = false)
+
+Same as `Jchemo.plskern` (src/plskern.jl:106-110): the inputs are left untouched.  No host copy of X
+is made (the reference's `copy` is replaced by the host-to-device transfer).
+"""
+function plskern(X, Y, weights = nothing; nlv, scal = false)
+    _fit(dense64(ensure_mat(X)), dense64(ensure_mat(Y)), weights, nlv, scal, false)
+end
+
+"""
+    plskern!(X::Matrix, Y::Matrix, weights = ones(nro(X)); nlv, scal = false)
+
+Same as `Jchemo.plskern!` (src/plskern.jl:112-178): X and Y leave centred (and scaled) in place.
+"""
+function plskern!(X::Matrix{Float64}, Y::Matrix{Float64}, weights = nothing; nlv, scal = false)
+    _fit(X, Y, weights, nlv, scal, true)
+end
+
+# ---------------------------------------------------------------- transform (src/plskern.jl:187-195)
+function transform(object::Plsr, X; nlv = nothing)
+    X = dense64(ensure_mat(X))
+    a = nco(object.T)
+    isnothing(nlv) ? nlv = a : nlv = min(nlv, a)
+    nlv = max(nlv, 0)
+    m, p = size(X)
+    p == nro(object.R) || throw(DimensionMismatch("X has $p columns, the model has $(nro(object.R))"))
+    T = Matrix{Float64}(undef, m, nlv)
+    (nlv == 0 || m == 0) && return T
+    rc = ccall((:jcb200_transform, LIB), Cint,
+               (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
+                Ptr{Float64}, Int64),
+               X, m, m, p, object.xmeans, object.xscales, object.R, nlv, T, m)
+    check(rc, "transform")
+    T
+end
+
+# ---------------------------------------------------------------- coef (src/plskern.jl:207-217)
+function coef(object::Plsr; nlv = nothing)
+    a = nco(object.T)
+    isnothing(nlv) ? nlv = a : nlv = min(nlv, a)
+    nlv = max(nlv, 0)
+    p = nro(object.R); q = nro(object.C)
+    B = Matrix{Float64}(undef, p, q)
+    int = Matrix{Float64}(undef, 1, q)
+    rc = ccall((:jcb200_coef, LIB), Cint,
+               (Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64,
+                Int64, Int32, Ptr{Float64}, Ptr{Float64}),
+               a == 0 ? C_NULL : object.R, a == 0 ? C_NULL : object.C, object.xmeans, object.xscales,
+               object.ymeans, object.yscales, p, q, nlv, B, int)
+    check(rc, "coef")
+    (B = B, int = int)
+end
+
+# ---------------------------------------------------------------- predict (src/plskern.jl:226-238)
+function predict(object::Plsr, X; nlv = nothing)
+    X = dense64(ensure_mat(X))
+    a = nco(object.T)
+    isnothing(nlv) ? nlv = a : nlv = (max(0, minimum(nlv)):min(a, maximum(nlv)))   # :229
+    le_nlv = length(nlv)
+    m, p = size(X)
+    q = nro(object.C)
+    p == length(object.xmeans) || throw(DimensionMismatch("X has $p columns"))
+    pred = [Matrix{Float64}(undef, m, q) for _ in 1:le_nlv]
+    if le_nlv > 0 && m > 0
+        ptrs = [pointer(z) for z in pred]
+        GC.@preserve pred begin
+            rc = ccall((:jcb200_predict_sweep, LIB), Cint,
+                       (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int32,
+                        Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32,
+                        Ptr{Ptr{Float64}}),
+                       X, m, m, p, q, a == 0 ? C_NULL : object.R, a == 0 ? C_NULL : object.C, a,
+                       object.xmeans, object.xscales, object.ymeans, object.yscales,
+                       first(nlv), last(nlv), ptrs)
+        end
+        check(rc, "predict")
+    end
+    le_nlv == 1 ? (pred = pred[1],) : (pred = pred,)                                # :236-237
+end
+
+end # module
