@@ -2,6 +2,7 @@
 // include/jchemo_b200.h.  No C++ exception crosses the boundary; there is no CPU fallback.
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -53,6 +54,14 @@ void phase_begin(Ctx* c, int ph) {
 }
 void phase_end(Ctx* c, int ph) {
     cudaEventRecord(c->ev_end[ph], c->stream);
+    c->ev_used[ph] = true;
+}
+void phase_begin_on(Ctx* c, int ph, cudaStream_t st) {
+    if (!c->ev_used[ph]) cudaEventRecord(c->ev_begin[ph], st);
+    c->ev_used[ph] = true;
+}
+void phase_end_on(Ctx* c, int ph, cudaStream_t st) {
+    cudaEventRecord(c->ev_end[ph], st);
     c->ev_used[ph] = true;
 }
 static void phases_reset(Ctx* c) {
@@ -111,6 +120,7 @@ static int init_locked(int device) {
         c->ev_used[i] = false;
         c->last_ms[i] = 0.0;
     }
+    for (int i = 0; i < 3; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
         JCB_CUDA(cudaEventCreate(&c->gram_ev0[i]));
         JCB_CUDA(cudaEventCreate(&c->gram_ev1[i]));
@@ -224,6 +234,7 @@ void jcb200_shutdown(void) {
     free_buf(c->hT);
     free_buf(c->hSmall);
     free_buf(c->hPred);
+    free_staging(c);
     if (c->sched_host) cudaFreeHost(c->sched_host);
     c->sched_host = nullptr;
     c->sched_host_bytes = 0;
@@ -232,6 +243,7 @@ void jcb200_shutdown(void) {
         cudaEventDestroy(c->ev_begin[i]);
         cudaEventDestroy(c->ev_end[i]);
     }
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(c->chunk_ev[i]);
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
         cudaEventDestroy(c->gram_ev0[i]);
         cudaEventDestroy(c->gram_ev1[i]);
@@ -437,21 +449,49 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     double* dym = cv.take(q);
     double* dys = cv.take(q);
 
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->stream, cs = c->copy_stream;
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
-    phase_begin(c, JCB200_T_H2D);
-    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, n * 8, p, cudaMemcpyHostToDevice, st));
-    JCB_CUDA(cudaMemcpy2DAsync(dY, ld * 8, Y, ldy * 8, n * 8, q, cudaMemcpyHostToDevice, st));
-    if (w) JCB_CUDA(cudaMemcpyAsync(dw, w, n * 8, cudaMemcpyHostToDevice, st));
-    phase_end(c, JCB200_T_H2D);
-
-    JCB_TRY(fit_dev_locked(c, dX, ld, dY, ld, dw, n, p, q, nlv, scal, writeback_xy, dT, ld, dP, dR,
-                           dW, dC, dTT, dxm, dxs, dym, dys, dwout, d_pivot, d_packed, d_sumw));
+    // ---- rows are streamed in chunks: the copy of chunk i+1 (copy stream) overlaps K1 on chunk i
+    // (compute stream); the partial Grams accumulate in the packed buffer.  The pivot comes from chunk 0.
+    int64_t chunk = n;
+    if (n >= 400000) {
+        chunk = (n + 7) / 8;
+        chunk = (chunk + 1) & ~(int64_t)1;              // shards stay 16-byte aligned
+    }
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));      // copies must not overtake earlier work on `st`
+    JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
+    phase_begin_on(c, JCB200_T_H2D, cs);
+    if (w) JCB_TRY(h2d_2d(c, dw, ld, w, n, n, 1, cs));
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int64_t r0 = (int64_t)ci * chunk, nr = std::min(chunk, n - r0);
+        JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
+        JCB_TRY(h2d_2d(c, dY + r0, ld, Y + r0, ldy, nr, q, cs));
+        if (ci == nchunks - 1) phase_end_on(c, JCB200_T_H2D, cs);
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
+        JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1 + (ci & 1)], 0));
+        if (ci == 0) {
+            phase_begin(c, JCB200_T_PIVOT);
+            JCB_TRY(launch_pivot(c, dX, ld, dY, ld, nr, p, q, d_pivot));
+            phase_end(c, JCB200_T_PIVOT);
+        }
+        JCB_TRY(launch_gram(c, dX + r0, ld, dY + r0, ld, dw ? dw + r0 : nullptr, nr, p, q, d_pivot,
+                            d_packed, ci > 0));
+    }
+    JCB_TRY(launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxm, dxs, dym, dys,
+                         d_sumw));
+    if (nlv > 0) JCB_TRY(launch_xmul(c, dX, ld, n, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
+    JCB_TRY(launch_weights(c, dw, n, d_sumw, dwout));
+    if (writeback_xy) {
+        phase_begin(c, JCB200_T_WRITEBACK);
+        JCB_TRY(launch_center_scale(c, dX, ld, n, p, dxm, dxs));
+        JCB_TRY(launch_center_scale(c, dY, ld, n, q, dym, dys));
+        phase_end(c, JCB200_T_WRITEBACK);
+    }
 
     phase_begin(c, JCB200_T_D2H);
     if (nlv > 0) {
-        JCB_CUDA(cudaMemcpy2DAsync(T, ldt * 8, dT, ld * 8, n * 8, nlv, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(W, dW, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
@@ -462,10 +502,11 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
-    JCB_CUDA(cudaMemcpyAsync(w_out, dwout, n * 8, cudaMemcpyDeviceToHost, st));
+    if (nlv > 0) JCB_TRY(d2h_2d(c, T, ldt, dT, ld, n, nlv, st));
+    JCB_TRY(d2h_2d(c, w_out, n, dwout, ld, n, 1, st));
     if (writeback_xy) {
-        JCB_CUDA(cudaMemcpy2DAsync(X, ldx * 8, dX, ld * 8, n * 8, p, cudaMemcpyDeviceToHost, st));
-        JCB_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, dY, ld * 8, n * 8, q, cudaMemcpyDeviceToHost, st));
+        JCB_TRY(d2h_2d(c, X, ldx, dX, ld, n, p, st));
+        JCB_TRY(d2h_2d(c, Y, ldy, dY, ld, n, q, st));
     }
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
@@ -496,14 +537,14 @@ int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const d
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
     phase_begin(c, JCB200_T_H2D);
-    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, m * 8, p, cudaMemcpyHostToDevice, st));
+    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
     JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
     phase_end(c, JCB200_T_H2D);
     JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
     phase_begin(c, JCB200_T_D2H);
-    JCB_CUDA(cudaMemcpy2DAsync(T_out, ldt * 8, dT, ld * 8, m * 8, nlv, cudaMemcpyDeviceToHost, st));
+    JCB_TRY(d2h_2d(c, T_out, ldt, dT, ld, m, nlv, st));
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
@@ -576,7 +617,7 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
     phase_begin(c, JCB200_T_H2D);
-    JCB_CUDA(cudaMemcpy2DAsync(dX, ld * 8, X, ldx * 8, m * 8, p, cudaMemcpyHostToDevice, st));
+    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
     if (a > 0) {
         JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * a * 8, cudaMemcpyHostToDevice, st));
         JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * a * 8, cudaMemcpyHostToDevice, st));
@@ -596,9 +637,7 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
                                      dPred));
     }
     phase_begin(c, JCB200_T_D2H);
-    for (int i = 0; i < nk; ++i)
-        JCB_CUDA(cudaMemcpyAsync(pred_out[i], dPred + (size_t)i * m * q, (size_t)m * q * 8,
-                                 cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < nk; ++i) JCB_TRY(d2h_2d(c, pred_out[i], m, dPred + (size_t)i * m * q, m, m, q, st));
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));

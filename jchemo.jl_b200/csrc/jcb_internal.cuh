@@ -73,6 +73,10 @@ struct Ctx {
     static constexpr int GRAM_RING = 256;
     cudaEvent_t gram_ev0[GRAM_RING], gram_ev1[GRAM_RING];
     int64_t gram_calls = 0;
+    // pinned staging slots for pageable host arrays (hostcopy.cu)
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2];
+    cudaEvent_t chunk_ev[3];
     // timing
     cudaEvent_t ev_begin[JCB200_NPHASE], ev_end[JCB200_NPHASE];
     bool ev_used[JCB200_NPHASE];
@@ -82,6 +86,13 @@ struct Ctx {
 Ctx* ctx();                               // the process-wide context (API mutex must be held)
 int ensure(Buf& b, size_t bytes);         // grow-only cudaMalloc
 void phase_begin(Ctx* c, int ph);
+void phase_begin_on(Ctx* c, int ph, cudaStream_t st);
+void phase_end_on(Ctx* c, int ph, cudaStream_t st);
+int h2d_2d(Ctx* c, double* dDst, int64_t ldd, const double* hSrc, int64_t lds, int64_t rows, int64_t cols,
+           cudaStream_t st);
+int d2h_2d(Ctx* c, double* hDst, int64_t ldd, const double* dSrc, int64_t lds, int64_t rows, int64_t cols,
+           cudaStream_t st);
+void free_staging(Ctx* c);
 void phase_end(Ctx* c, int ph);
 
 // ---------------------------------------------------------------- kernel launchers
