@@ -113,6 +113,17 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
                          const double* ymeans, const double* yscales,
                          int32_t k_lo, int32_t k_hi, double* const* pred_out);
 
+/* gridscorelv fused scoring (next row) — /root/reference/src/gridscore.jl:179-185 with
+ * the scores of src/scores.jl (msep :155-158, rmsep :268, ssr :426-429, bias :25-28, sep :400, r2
+ * :190-195, rpd :332-335): for every k in k_lo..k_hi the residual sums of the validation set (X, Y)
+ *   ssr[i + j*nk]    = sum_rows (Y[:, j] - pred_k[:, j])^2 ,   sumres[i + j*nk] = sum_rows (Y[:, j] - pred_k[:, j])
+ * (k = k_lo + i, nk = k_hi - k_lo + 1, column-major nk x q), plus ysum[j] = sum Y[:, j] and
+ * ysumsq[j] = sum Y[:, j]^2, in one pass over X and without materialising any prediction. */
+int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t m, int64_t p,
+                     int64_t q, const double* R, const double* C, int32_t a, const double* xmeans,
+                     const double* xscales, const double* ymeans, const double* yscales, int32_t k_lo,
+                     int32_t k_hi, double* ssr, double* sumres, double* ysum, double* ysumsq);
+
 /* ---- device-pointer entry points (staged fit; one process per GPU shards rows) ------------- */
 
 /* Length (doubles) of the packed partial-Gram buffer [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw 1]:

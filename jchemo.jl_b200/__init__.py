@@ -8,5 +8,7 @@ from ._lib import JchemoB200Error, lib, last_timings, LIB_PATH, SIGNATURES  # no
 from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict,  # noqa: F401
                       ensure_mat, CoefResult, PredResult)
 
-__all__ = ["Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "ensure_mat",
+from .gridscore import gridscorelv, residual_sums  # noqa: F401
+
+__all__ = ["gridscorelv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "ensure_mat",
            "JchemoB200Error", "lib", "last_timings"]

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "jcb_internal.cuh"
 
@@ -642,6 +643,68 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);
+    return 0;
+}
+
+int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t m, int64_t p,
+                     int64_t q, const double* R, const double* C, int32_t a, const double* xmeans,
+                     const double* xscales, const double* ymeans, const double* yscales, int32_t k_lo,
+                     int32_t k_hi, double* ssr, double* sumres, double* ysum, double* ysumsq) {
+    API_PROLOGUE();
+    ARG_CHECK(X && Y && xmeans && xscales && ymeans && yscales && ssr && sumres && ysum && ysumsq &&
+                  m > 0 && p > 0 && q > 0 && ldx >= m && ldy >= m && a >= 0 && k_lo >= 0 &&
+                  k_hi >= k_lo && k_hi <= a,
+              "gridscore: bad argument");
+    ARG_CHECK(a == 0 || (R && C), "gridscore: NULL model");
+    const int ka = k_hi > 0 ? k_hi : 1;
+    const int64_t ld = even_up(m);
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    JCB_TRY(ensure(c->hT, (size_t)ld * ka * 8));
+    JCB_TRY(ensure(c->hPred, (size_t)ld * 2 * q * 8));
+    const int64_t plen = packed_len(ka, 2 * q);
+    const size_t nd = (size_t)p * a + (size_t)q * a + 2 * (p + q) + plen + (ka + 2 * q + 1) + 64;
+    JCB_TRY(ensure(c->hSmall, nd * 8));
+    double* dX = (double*)c->hX.p;
+    double* dY = (double*)c->hY.p;
+    double* dT = (double*)c->hT.p;
+    double* dYaug = (double*)c->hPred.p;
+    Carver cv(c->hSmall.p);
+    double* dR = cv.take((size_t)p * a);
+    double* dC = cv.take((size_t)q * a);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dym = cv.take(q);
+    double* dys = cv.take(q);
+    double* dpk = cv.take(plen);
+    double* dpv = cv.take(ka + 2 * q + 1);
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
+    JCB_TRY(h2d_2d(c, dY, ld, Y, ldy, m, q, st));
+    if (a > 0) {
+        JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * a * 8, cudaMemcpyHostToDevice, st));
+        JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * a * 8, cudaMemcpyHostToDevice, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dym, ymeans, q * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dys, yscales, q * 8, cudaMemcpyHostToDevice, st));
+    phase_end(c, JCB200_T_H2D);
+    if (k_hi > 0) {
+        JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, k_hi, nullptr, dT, ld));
+    } else {
+        JCB_CUDA(cudaMemsetAsync(dT, 0, (size_t)ld * 8, st));
+    }
+    JCB_TRY(launch_gridscore_gram(c, dY, ld, dT, ld, dC, dys, dym, m, (int)q, k_hi, ka, dYaug, ld, dpv, dpk));
+    std::vector<double> hpk((size_t)plen);
+    JCB_CUDA(cudaMemcpyAsync(hpk.data(), dpk, (size_t)plen * 8, cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    gridscore_from_packed(hpk.data(), ka, (int)q, k_lo, k_hi, C, yscales, ssr, sumres, ysum, ysumsq);
     return 0;
 }
 

@@ -121,6 +121,12 @@ int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmean
                 const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
                 int64_t q, int k, double* dB, double* dint);
 
+int launch_gridscore_gram(Ctx* c, const double* dY, int64_t ldy, const double* dT, int64_t ldt,
+                          const double* dC, const double* dys, const double* dymeans, int64_t m, int q,
+                          int k_hi, int ka, double* dYaug, int64_t lda, double* d_pivot0, double* d_packed);
+void gridscore_from_packed(const double* pk, int ka, int q, int k_lo, int k_hi, const double* C,
+                           const double* ys, double* ssr, double* sumres, double* ysum, double* ysumsq);
+
 inline int64_t packed_len(int64_t p, int64_t q) { return p * p + p * q + q + p + q + 1; }
 // offsets into the packed buffer
 inline int64_t off_gxy(int64_t p, int64_t q) { return p * p; }

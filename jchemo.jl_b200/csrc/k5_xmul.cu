@@ -79,11 +79,14 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
     unsigned char* stage_base = smem;
     double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NP][132]
     double* mu_s = out_s + NP * XM_PITCH;                                        // nchunk*32
-    uint64_t* full = reinterpret_cast<uint64_t*>(mu_s + prm.nchunk * XM_KC);
+    double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0));
     uint64_t* empty = full + nstage;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < prm.nchunk * XM_KC; k += XM_THREADS) mu_s[k] = prm.mu[k];
+    if (SWEEP)
+        for (int k = threadIdx.x; k < prm.ncol * prm.q; k += XM_THREADS) cy_s[k] = prm.Cy[k];
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
@@ -193,15 +196,29 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                 }
             }
         } else {
-            // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]
+            // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]: k outer, up to 8 responses
+            // per lane carried in registers (independent chains), Cy from shared memory
             const int q = prm.q;
             const int64_t msz = prm.m * (int64_t)q;
-            for (int j = half; j < q; j += 2) {
-                double pv = prm.ymeans[j];
+            for (int j0 = half; j0 < q; j0 += 16) {
+                double pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pv[u] = (j0 + 2 * u < q) ? prm.ymeans[j0 + 2 * u] : 0.0;
+                double* dst = prm.Pred + row0 + m0 + r;
                 for (int k = 0; k <= prm.k_hi; ++k) {
-                    if (k >= prm.k_lo && rok)
-                        prm.Pred[(int64_t)(k - prm.k_lo) * msz + row0 + m0 + r + (int64_t)j * prm.m] = pv;
-                    if (k < prm.k_hi) pv += out_s[k * XM_PITCH + m0 + r] * prm.Cy[k * q + j];
+                    if (k >= prm.k_lo && rok) {
+                        double* dk = dst + (int64_t)(k - prm.k_lo) * msz;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j0 + 2 * u < q) dk[(int64_t)(j0 + 2 * u) * prm.m] = pv[u];
+                    }
+                    if (k < prm.k_hi) {
+                        const double t = out_s[k * XM_PITCH + m0 + r];
+                        const double* cy = cy_s + k * q + j0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j0 + 2 * u < q) pv[u] += t * cy[2 * u];
+                    }
                 }
             }
         }
@@ -222,7 +239,8 @@ template <int NPB, bool SWEEP>
 static int launch_xmul_t(Ctx* c, XmulParams& prm) {
     constexpr int NP = NPB * 8;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
-    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128;
+    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
+                      (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
     int nstage = (int)((220 * 1024 - fixed) / stage);
     if (nstage > 4) nstage = 4;
     if (nstage < 2) {

@@ -17,7 +17,7 @@ module JchemoB200
 using LinearAlgebra
 using Libdl
 
-export Plsr, plskern, plskern!, transform, coef, predict
+export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv
 
 const LIB = get(ENV, "JCHEMO_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
@@ -163,6 +163,42 @@ function predict(object::Plsr, X; nlv = nothing)
         check(rc, "predict")
     end
     le_nlv == 1 ? (pred = pred[1],) : (pred = pred,)                                # :236-237
+end
+
+# ---------------------------------------------------------------- gridscorelv (src/gridscore.jl:167-221)
+"""
+    gridscorelv(Xtrain, Ytrain, X, Y; score, nlv, kwargs...)
+
+`Jchemo.gridscorelv` for `fun = plskern` (branch `pars === nothing`): one fit with `maximum(nlv)` LVs,
+then the residual sums of the validation set for every nlv in ONE pass on the GPU
+(`jcb200_gridscore`); `score` is one of `:msep, :rmsep, :ssr, :bias, :sep, :r2, :rpd`
+(src/scores.jl).  Returns a NamedTuple of columns `nlv, y1, ..., yq` (wrap in `DataFrame` as needed).
+"""
+function gridscorelv(Xtrain, Ytrain, X, Y; score::Symbol, nlv, kwargs...)
+    Xtrain = dense64(ensure_mat(Xtrain)); Ytrain = dense64(ensure_mat(Ytrain))
+    X = dense64(ensure_mat(X)); Y = dense64(ensure_mat(Y))
+    p = nco(Xtrain)
+    lo = max(0, minimum(nlv)); hi = min(p, maximum(nlv))                 # :170-173
+    fm = plskern(Xtrain, Ytrain; nlv = hi, kwargs...)                    # :179
+    a = nco(fm.T); hi = min(hi, a); nk = hi - lo + 1
+    m = nro(X); q = nco(Y)
+    ssr = Matrix{Float64}(undef, nk, q); sres = similar(ssr)
+    ysum = Vector{Float64}(undef, q); ysumsq = similar(ysum)
+    rc = ccall((:jcb200_gridscore, LIB), Cint,
+               (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64},
+                Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               X, m, Y, m, m, p, q, a == 0 ? C_NULL : fm.R, a == 0 ? C_NULL : fm.C, a, fm.xmeans,
+               fm.xscales, fm.ymeans, fm.yscales, lo, hi, ssr, sres, ysum, ysumsq)
+    check(rc, "gridscorelv")
+    ms = ssr ./ m; bi = -sres ./ m
+    vary = (ysumsq ./ m .- (ysum ./ m) .^ 2)'
+    res = score === :msep ? ms : score === :rmsep ? sqrt.(ms) : score === :ssr ? ssr :
+          score === :bias ? bi : score === :sep ? sqrt.(ms .- bi .^ 2) :
+          score === :r2 ? 1 .- ms ./ vary : score === :rpd ? sqrt.(vary) ./ sqrt.(ms) :
+          error("score must be one of :msep, :rmsep, :ssr, :bias, :sep, :r2, :rpd")
+    cols = (; nlv = collect(lo:hi), (Symbol("y", j) => res[:, j] for j in 1:q)...)
+    cols
 end
 
 end # module

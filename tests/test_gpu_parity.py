@@ -155,3 +155,33 @@ def test_full_size_properties(jc):
     assert relerr(jc.coef(fm2).B, jc.coef(fm).B) < TOL
     s = np.sign(np.sum(fm.W * fm2.W, axis=0))
     assert relerr((fm2.T * s)[np.argsort(perm)][rows], fm.T[rows]) < 1e-9
+
+
+@pytest.mark.parametrize("score", ["msep", "rmsep", "ssr", "bias", "sep", "r2", "rpd"])
+def test_gridscorelv_fused_scores(jc, score):
+    """Next row: gridscorelv for fun = plskern, every nlv scored on the device in one pass,
+    against the oracle's fit + predict + score loop (gridscore.jl:167-221, scores.jl)."""
+    n, m, p, q, nlv = 3000, 1201, 150, 3, 12
+    Xtr = synth.synth_matrix(1, n, p)
+    Ytr = synth.synth_matrix(2, n, q) + Xtr[:, :q] * 2.0 + Xtr[:, q:2 * q]
+    Xte = synth.synth_matrix(4, m, p)
+    Yte = synth.synth_matrix(5, m, q) + Xte[:, :q] * 2.0 + Xte[:, q:2 * q]
+    got = jc.gridscorelv(Xtr, Ytr, Xte, Yte, score=score, nlv=range(0, nlv + 1))
+    ref = oracle.gridscorelv(Xtr, Ytr, Xte, Yte, score=score, nlv=range(0, nlv + 1))
+    assert list(got["nlv"]) == list(ref["nlv"]) == list(range(nlv + 1))
+    for j in range(q):
+        g, r = np.asarray(got[f"y{j + 1}"]), ref[f"y{j + 1}"]
+        tol = 1e-9 if score == "bias" else TOL       # bias is a difference of means: absolute scale
+        assert np.linalg.norm(g - r) <= tol * max(np.linalg.norm(r), 1e-3), (score, j)
+
+
+def test_gridscorelv_ranges_and_vector_y(jc):
+    X = synth.synth_matrix(1, 400, 20)
+    y = synth.synth_matrix(2, 400, 1)[:, 0] + X[:, 0]
+    got = jc.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="rmsep", nlv=[2, 5])   # widened to 2:5
+    ref = oracle.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="rmsep", nlv=[2, 5])
+    assert list(got["nlv"]) == [2, 3, 4, 5]
+    assert relerr(np.asarray(got["y1"]), ref["y1"]) < TOL
+    got0 = jc.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="msep", nlv=0)         # nlv = 0 only
+    ref0 = oracle.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="msep", nlv=0)
+    assert relerr(np.asarray(got0["y1"]), ref0["y1"]) < TOL

@@ -128,3 +128,16 @@ def test_longdouble_truth_small():
     B_ld = (np.stack(Rs, 1) @ np.stack(Cs, 1).T).astype(np.float64)
     fm = oracle.plskern(X.astype(np.float64), Y.astype(np.float64), nlv=nlv)
     assert relerr(oracle.coef(fm)[0], B_ld) < 1e-12
+
+
+def test_gridscorelv_oracle_matches_direct_loop():
+    """oracle.gridscorelv (gridscore.jl:167-221) against an explicit fit / predict / score loop."""
+    X = synth.synth_matrix(1, 300, 12)
+    Y = synth.synth_matrix(2, 300, 2) + X[:, :2]
+    out = oracle.gridscorelv(X[:200], Y[:200], X[200:], Y[200:], score="rmsep", nlv=range(0, 6))
+    fm = oracle.plskern(X[:200], Y[:200], nlv=5)
+    for k in range(6):
+        pr = oracle.predict(fm, X[200:], nlv=k)
+        np.testing.assert_allclose([out["y1"][k], out["y2"][k]],
+                                   np.sqrt(np.mean((Y[200:] - pr) ** 2, axis=0)), rtol=1e-13)
+    assert list(out["nlv"]) == [0, 1, 2, 3, 4, 5]
