@@ -185,3 +185,53 @@ def test_gridscorelv_ranges_and_vector_y(jc):
     got0 = jc.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="msep", nlv=0)         # nlv = 0 only
     ref0 = oracle.gridscorelv(X[:300], y[:300], X[300:], y[300:], score="msep", nlv=0)
     assert relerr(np.asarray(got0["y1"]), ref0["y1"]) < TOL
+
+
+def test_c4_shape_cut(jc):
+    """BASELINE C4's column shape (p=2000, q=10, nlv=50) on a row cut: more Gram groups than SMs, XtY too
+    large for shared memory in the LV loop (global path, two cluster barriers per LV), 63 column chunks
+    in the score kernel."""
+    n, p, q, nlv, m = 6001, 2000, 10, 50, 333
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q) + X[:, :q] - X[:, q:2 * q]
+    Xnew = synth.synth_matrix(4, m, p)
+    fm = jc.plskern(X, Y, nlv=nlv)
+    ref = oracle.plskern(X, Y, nlv=nlv)
+    s = oracle.sign_align(ref, fm)
+    assert relerr(fm.T * s, ref.T) < TOL
+    assert relerr(fm.R * s, ref.R) < TOL
+    assert relerr(jc.coef(fm).B, oracle.coef(ref)[0]) < TOL
+    pr = jc.predict(fm, Xnew, nlv=range(0, nlv + 1)).pred
+    rr = oracle.predict(ref, Xnew, nlv=range(0, nlv + 1))
+    assert max(relerr(a, b) for a, b in zip(pr, rr)) < TOL
+
+
+def test_wide_y_and_many_lvs(jc):
+    """q > 32 (several Y blocks, generic eigen path) and nlv > 64 (two passes of the score kernel)."""
+    n, p, q, nlv = 2000, 150, 40, 70
+    X = synth.synth_matrix(1, n, p)
+    Y = synth.synth_matrix(2, n, q) + X[:, :q]
+    fm = jc.plskern(X, Y, nlv=nlv, scal=True)
+    ref = oracle.plskern(X, Y, nlv=nlv, scal=True)
+    s = oracle.sign_align(ref, fm)
+    ok = np.arange(nlv) < 40          # beyond rank(Y'X) = q the kernel is rounding noise in the reference too
+    assert relerr((fm.T * s)[:, ok], ref.T[:, ok]) < TOL
+    assert relerr(jc.coef(fm, nlv=40).B, oracle.coef(ref, nlv=40)[0]) < TOL
+    assert relerr(jc.transform(fm, X[:100], nlv=40) * s[:40], oracle.transform(ref, X[:100], nlv=40)) < TOL
+
+
+def test_device_api_rejects_misaligned(jc):
+    import ctypes as C
+    import torch
+    from jchemo_b200 import device as dev, _lib
+    dev.init(0)
+    X = torch.zeros(7 * 101 + 8, dtype=torch.float64, device="cuda")
+    Y = torch.zeros(101 + 8, dtype=torch.float64, device="cuda")
+    piv = torch.zeros(9, dtype=torch.float64, device="cuda")
+    pk = torch.zeros(int(_lib.lib().jcb200_packed_len(7, 1)), dtype=torch.float64, device="cuda")
+    rc = _lib.lib().jcb200_gram_dev(C.c_void_p(X.data_ptr()), 101, C.c_void_p(Y.data_ptr()), 101, None,
+                                    100, 7, 1, C.c_void_p(piv.data_ptr()), C.c_void_p(pk.data_ptr()), 0)
+    assert rc == -4 and b"aligned" in _lib.lib().jcb200_last_error()          # JCB200_EALIGN: odd ld
+    rc = _lib.lib().jcb200_gram_dev(None, 100, C.c_void_p(Y.data_ptr()), 100, None, 100, 7, 1,
+                                    C.c_void_p(piv.data_ptr()), C.c_void_p(pk.data_ptr()), 0)
+    assert rc == -1                                                            # JCB200_EINVAL
