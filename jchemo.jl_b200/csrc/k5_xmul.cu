@@ -68,17 +68,21 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
         mu_pad[k] = k < p ? mu[k] : 0.0;
 }
 
-template <int NPB, bool SWEEP>
+template <int NPB, int NEX, bool SWEEP>
 __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams prm) {
+    // NPB column blocks go through DMMA; NEX (<= 2) leftover columns are plain DFMA dot products on the
+    // A fragments this lane already holds (a whole padded 8-column block for 1-2 columns would cost
+    // 1/NPB more DMMA time: at nlv = 25 the score GEMM drops from 4 to 3 blocks)
     constexpr int NP = NPB * 8;
+    constexpr int NPT = NP + NEX;
     constexpr int XBYTES = XM_KC * XM_PITCH * 8;        // 33792
-    constexpr int MBYTES = NP * XM_MPITCH * 8;
+    constexpr int MBYTES = NPT * XM_MPITCH * 8;
     constexpr int STAGE = XBYTES + MBYTES;
     extern __shared__ __align__(128) unsigned char smem[];
     const int nstage = prm.nstage;
     unsigned char* stage_base = smem;
-    double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NP][132]
-    double* mu_s = out_s + NP * XM_PITCH;                                        // nchunk*32
+    double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NPT][132]
+    double* mu_s = out_s + NPT * XM_PITCH;                                        // nchunk*32
     double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
     uint64_t* full = reinterpret_cast<uint64_t*>(cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0));
     uint64_t* empty = full + nstage;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                 __syncwarp();
                 double* xs = reinterpret_cast<double*>(stage_base + (size_t)buf * STAGE);
                 double* ms = xs + XM_KC * XM_PITCH;
-                const double* msrc = prm.Mt + (int64_t)ch * NP * XM_MPITCH;
+                const double* msrc = prm.Mt + (int64_t)ch * NPT * XM_MPITCH;
                 if (bulk) {
                     if (lane == 0) mbar_arrive_expect_tx(&full[buf], XM_KC * crow * 8 + MBYTES);
                     __syncwarp();
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                             xs[kc * XM_PITCH + r] =
                                 (k < prm.p && r < rows) ? prm.X[row0 + r + (int64_t)k * prm.ldx] : 0.0;
                     }
-                    for (int e = lane; e < NP * XM_MPITCH; e += 32) ms[e] = msrc[e];
+                    for (int e = lane; e < NPT * XM_MPITCH; e += 32) ms[e] = msrc[e];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[buf]);   // release: generic-proxy writes above
                 }
@@ -148,10 +152,14 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
         const int64_t row0 = t * XM_MT;
         const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
         double acc[2][NPB][2];
+        double ex[2][NEX > 0 ? NEX : 1];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int nb = 0; nb < NPB; ++nb) acc[h][nb][0] = acc[h][nb][1] = 0.0;
+#pragma unroll
+            for (int e = 0; e < NEX; ++e) ex[h][e] = 0.0;
+        }
         for (int ch = 0; ch < nchunk; ++ch, ++it) {
             const int buf = it % nstage;
             const uint32_t ph = (it / nstage) & 1;
@@ -172,6 +180,12 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                     dmma(acc[0][nb][0], acc[0][nb][1], a.x, b);
                     dmma(acc[1][nb][0], acc[1][nb][1], a.y, b);
                 }
+#pragma unroll
+                for (int e = 0; e < NEX; ++e) {
+                    const double b = ms[(NP + e) * XM_MPITCH + k];
+                    ex[0][e] += a.x * b;
+                    ex[1][e] += a.y * b;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[buf]);
@@ -183,6 +197,15 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
             for (int nb = 0; nb < NPB; ++nb) {
                 out_s[(nb * 8 + 2 * kk) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][0];
                 out_s[(nb * 8 + 2 * kk + 1) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][1];
+            }
+#pragma unroll
+        for (int e = 0; e < NEX; ++e)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double v = ex[h][e];                      // partial over this lane's k (kk); sum the 4 kk lanes
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (kk == 0) out_s[(NP + e) * XM_PITCH + m0 + 2 * g + h] = v;
             }
         __syncwarp();
         const int r = lane & 15, half = lane >> 4;
@@ -235,9 +258,9 @@ __global__ void sweep_cy_kernel(const double* __restrict__ C, const double* __re
     Cy[e] = C[j + (int64_t)k * q] * ys[j];
 }
 
-template <int NPB, bool SWEEP>
+template <int NPB, int NEX, bool SWEEP>
 static int launch_xmul_t(Ctx* c, XmulParams& prm) {
-    constexpr int NP = NPB * 8;
+    constexpr int NP = NPB * 8 + NEX;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
     const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
                       (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
@@ -249,27 +272,33 @@ static int launch_xmul_t(Ctx* c, XmulParams& prm) {
     }
     prm.nstage = nstage;
     const int smem = nstage * stage + fixed;
-    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem));
     const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
     const int grid = (int)std::min<int64_t>(ntiles, c->num_sms);
-    xmul_kernel<NPB, SWEEP><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+    xmul_kernel<NPB, NEX, SWEEP><<<grid, XM_THREADS, smem, c->stream>>>(prm);
     JCB_LAUNCH_CHECK();
     return 0;
 }
 
-template <bool SWEEP>
-static int dispatch_xmul(Ctx* c, XmulParams& prm, int npb) {
+template <bool SWEEP, int NEX>
+static int dispatch_xmul_n(Ctx* c, XmulParams& prm, int npb) {
     switch (npb) {
-        case 1: return launch_xmul_t<1, SWEEP>(c, prm);
-        case 2: return launch_xmul_t<2, SWEEP>(c, prm);
-        case 3: return launch_xmul_t<3, SWEEP>(c, prm);
-        case 4: return launch_xmul_t<4, SWEEP>(c, prm);
-        case 5: return launch_xmul_t<5, SWEEP>(c, prm);
-        case 6: return launch_xmul_t<6, SWEEP>(c, prm);
-        case 7: return launch_xmul_t<7, SWEEP>(c, prm);
-        default: return launch_xmul_t<8, SWEEP>(c, prm);
+        case 1: return launch_xmul_t<1, NEX, SWEEP>(c, prm);
+        case 2: return launch_xmul_t<2, NEX, SWEEP>(c, prm);
+        case 3: return launch_xmul_t<3, NEX, SWEEP>(c, prm);
+        case 4: return launch_xmul_t<4, NEX, SWEEP>(c, prm);
+        case 5: return launch_xmul_t<5, NEX, SWEEP>(c, prm);
+        case 6: return launch_xmul_t<6, NEX, SWEEP>(c, prm);
+        case 7: return launch_xmul_t<7, NEX, SWEEP>(c, prm);
+        default: return launch_xmul_t<8, NEX, SWEEP>(c, prm);
     }
+}
+template <bool SWEEP>
+static int dispatch_xmul(Ctx* c, XmulParams& prm, int npb, int nex) {
+    if (nex == 1) return dispatch_xmul_n<SWEEP, 1>(c, prm, npb);
+    if (nex == 2) return dispatch_xmul_n<SWEEP, 2>(c, prm, npb);
+    return dispatch_xmul_n<SWEEP, 0>(c, prm, npb);
 }
 
 // workspace layout: zeros[128] | mu_pad | bias_pad[64] | Cy | Mt
@@ -285,7 +314,7 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
         return JCB200_EINVAL;
     }
     const size_t ws_doubles = 128 + (size_t)nchunk * XM_KC + 64 + (size_t)maxcol * (q > 0 ? q : 1) +
-                              (size_t)nchunk * maxcol * XM_MPITCH;
+                              (size_t)nchunk * (maxcol + 2) * XM_MPITCH;
     JCB_TRY(ensure(c->xmul_ws, ws_doubles * 8));
     double* zeros = (double*)c->xmul_ws.p;
     double* mu_pad = zeros + 128;
@@ -297,7 +326,13 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
 
     for (int c0 = 0; c0 < ncol_total; c0 += maxcol) {
         const int ncol = std::min(maxcol, ncol_total - c0);
-        const int npb = (ncol + 7) / 8, NP = npb * 8;
+        // full 8-column blocks by DMMA; 1-2 leftover columns by DFMA instead of a padded block
+        int npb = ncol / 8, nex = ncol % 8;
+        if (npb == 0 || nex > 2) {
+            npb = (ncol + 7) / 8;
+            nex = 0;
+        }
+        const int NP = npb * 8 + nex;
         xmul_pack_kernel<<<64, 256, 0, c->stream>>>(dM + (int64_t)c0 * ldm, ldm, dsigma, dmu, (int)p, ncol,
                                                     NP, nchunk, Mt, mu_pad);
         JCB_LAUNCH_CHECK();
@@ -325,9 +360,9 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
             prm.q = q;
             prm.k_lo = k_lo;
             prm.k_hi = k_hi;
-            JCB_TRY(dispatch_xmul<true>(c, prm, npb));
+            JCB_TRY(dispatch_xmul<true>(c, prm, npb, nex));
         } else {
-            JCB_TRY(dispatch_xmul<false>(c, prm, npb));
+            JCB_TRY(dispatch_xmul<false>(c, prm, npb, nex));
         }
     }
     return 0;

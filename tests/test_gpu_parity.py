@@ -235,3 +235,30 @@ def test_device_api_rejects_misaligned(jc):
     rc = _lib.lib().jcb200_gram_dev(None, 100, C.c_void_p(Y.data_ptr()), 100, None, 100, 7, 1,
                                     C.c_void_p(piv.data_ptr()), C.c_void_p(pk.data_ptr()), 0)
     assert rc == -1                                                            # JCB200_EINVAL
+
+
+def test_concurrent_callers(jc):
+    """The reference's callers invoke `fun` from Threads.@threads loops (src/locwlv.jl:18): entry points
+    must be re-entrant.  Four host threads fit different problems at once; each result must equal the
+    single-threaded one bit for bit (one mutex serialises the device work)."""
+    import threading
+    probs = []
+    for t in range(4):
+        n, p, q = 500 + 37 * t, 30 + t, 1 + (t % 3)
+        X = synth.synth_matrix(10 + t, n, p)
+        Y = synth.synth_matrix(20 + t, n, q) + X[:, :q]
+        probs.append((X, Y, 3 + t))
+    solo = [jc.plskern(X, Y, nlv=k) for X, Y, k in probs]
+    out = [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            X, Y, k = probs[i]
+            fm = jc.plskern(X, Y, nlv=k)
+            out[i] = (fm, jc.predict(fm, X[:7]).pred)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        assert np.array_equal(out[i][0].T, solo[i].T) and np.array_equal(out[i][0].R, solo[i].R)
+        assert np.array_equal(out[i][1], jc.predict(solo[i], probs[i][0][:7]).pred)
