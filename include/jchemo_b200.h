@@ -124,6 +124,14 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
                      const double* xscales, const double* ymeans, const double* yscales, int32_t k_lo,
                      int32_t k_hi, double* ssr, double* sumres, double* ysum, double* ysumsq);
 
+/* Base.summary(::Plsr, X) (next row) — /root/reference/src/plskern.jl:246-260: explained
+ * X-variance per LV.  One pass over X for sstot = sum(weights' * ((X - xmeans)./xscales).^2); then
+ * tt_adj = colsum(P.^2) .* TT, pvar = tt_adj / sstot, cumpvar = cumsum(pvar), xvar = tt_adj / n
+ * (a values each).  `weights` are the model's normalised weights (n). */
+int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const double* xmeans,
+                   const double* xscales, const double* weights, const double* P, const double* TT,
+                   int32_t a, double* xvar, double* pvar, double* cumpvar);
+
 /* ---- device-pointer entry points (staged fit; one process per GPU shards rows) ------------- */
 
 /* Length (doubles) of the packed partial-Gram buffer [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw 1]:

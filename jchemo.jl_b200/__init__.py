@@ -5,10 +5,10 @@ The compute lives in libjchemo_b200.so (hand-written sm_100a CUDA behind a C ABI
 include/jchemo_b200.h); this package is the host-side mirror of the reference's function API.
 """
 from ._lib import JchemoB200Error, lib, last_timings, LIB_PATH, SIGNATURES  # noqa: F401
-from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict,  # noqa: F401
+from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict, summary,  # noqa: F401
                       ensure_mat, CoefResult, PredResult)
 
 from .gridscore import gridscorelv, residual_sums  # noqa: F401
 
-__all__ = ["gridscorelv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "ensure_mat",
+__all__ = ["gridscorelv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "ensure_mat",
            "JchemoB200Error", "lib", "last_timings"]

@@ -708,6 +708,48 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
     return 0;
 }
 
+int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const double* xmeans,
+                   const double* xscales, const double* weights, const double* P, const double* TT,
+                   int32_t a, double* xvar, double* pvar, double* cumpvar) {
+    API_PROLOGUE();
+    ARG_CHECK(X && xmeans && xscales && weights && n > 0 && p > 0 && ldx >= n && a >= 0,
+              "summary: bad argument");
+    ARG_CHECK(a == 0 || (P && TT && xvar && pvar && cumpvar), "summary: NULL model or output");
+    const int64_t ld = even_up(n);
+    const int gx = 32;
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
+    JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + (size_t)gx * p + 16) * 8));
+    double* dX = (double*)c->hX.p;
+    double* dw = (double*)c->hW.p;
+    Carver cv(c->hSmall.p);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dpart = cv.take((size_t)gx * p);
+    double* dout = cv.take(2);
+    cudaStream_t st = c->stream;
+    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, n, p, st));
+    JCB_TRY(h2d_2d(c, dw, ld, weights, n, n, 1, st));
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_TRY(launch_sstot(c, dX, ld, n, p, dxm, dxs, dw, dpart, gx, dout));
+    double sstot = 0.0;
+    JCB_CUDA(cudaMemcpyAsync(&sstot, dout, 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaStreamSynchronize(st));
+    // tt_adj[l] = (p_l' p_l) tt_l ; pvar = tt_adj / sstot ; xvar = tt_adj / n      (plskern.jl:253-258)
+    double cum = 0.0;
+    for (int l = 0; l < a; ++l) {
+        double pp = 0.0;
+        for (int64_t i = 0; i < p; ++i) pp += P[i + (int64_t)l * p] * P[i + (int64_t)l * p];
+        const double tta = pp * TT[l];
+        pvar[l] = tta / sstot;
+        cum += pvar[l];
+        cumpvar[l] = cum;
+        xvar[l] = tta / (double)n;
+    }
+    return 0;
+}
+
 /* collect timings of the device-pointer entry points (call after synchronising the stream) */
 int jcb200_sync_timings(void) {
     API_PROLOGUE();

@@ -117,6 +117,8 @@ int launch_center_scale(Ctx* c, double* dX, int64_t ldx, int64_t n, int64_t p, c
 int launch_weights(Ctx* c, const double* dw, int64_t n, const double* dsumw, double* dw_out);
 int launch_fill_uniform(Ctx* c, double* d, int64_t ld, int64_t n_rows, int64_t n_cols,
                         uint64_t seed, int64_t row0, int64_t n_global);
+int launch_sstot(Ctx* c, const double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
+                 const double* dsigma, const double* dw, double* dpartial, int gx, double* dout);
 int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmeans,
                 const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
                 int64_t q, int k, double* dB, double* dint);

@@ -89,4 +89,56 @@ int launch_fill_uniform(Ctx* c, double* d, int64_t ld, int64_t n_rows, int64_t n
     return 0;
 }
 
+// summary(::Plsr, X) (/root/reference/src/plskern.jl:246-260): sstot = sum_ij w_i ((x_ij - mu_j)/sigma_j)^2,
+// the weighted total sum of squares of the centred/scaled X.  One HBM-bound pass; per-block partial sums
+// are written to `partial` and added in a fixed order by the last kernel (deterministic).
+__global__ void __launch_bounds__(256)
+sstot_partial_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int p,
+                     const double* __restrict__ mu, const double* __restrict__ sigma,
+                     const double* __restrict__ w, double* __restrict__ partial) {
+    const int j = blockIdx.y;
+    const double m = mu[j], is = 1.0 / sigma[j];
+    const double* col = X + (int64_t)j * ldx;
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double d = (col[i] - m) * is;
+        s += w[i] * d * d;
+    }
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        partial[(int64_t)j * gridDim.x + blockIdx.x] = t;
+    }
+}
+__global__ void sstot_final_kernel(const double* __restrict__ partial, int64_t count, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) s += partial[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+        *out = t;
+    }
+}
+
+int launch_sstot(Ctx* c, const double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
+                 const double* dsigma, const double* dw, double* dpartial, int gx, double* dout) {
+    dim3 grid(gx, (unsigned)p);
+    sstot_partial_kernel<<<grid, 256, 0, c->stream>>>(dX, ldx, n, (int)p, dmu, dsigma, dw, dpartial);
+    JCB_LAUNCH_CHECK();
+    sstot_final_kernel<<<1, 1024, 0, c->stream>>>(dpartial, (int64_t)gx * p, dout);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace jcb

@@ -165,6 +165,27 @@ function predict(object::Plsr, X; nlv = nothing)
     le_nlv == 1 ? (pred = pred[1],) : (pred = pred,)                                # :236-237
 end
 
+# ---------------------------------------------------------------- summary (src/plskern.jl:246-260)
+"""
+    summary(object::Plsr, X)
+
+Explained X-variance per LV, as `Jchemo`'s `Base.summary(::Plsr, X)`: returns
+`(explvarx = (nlv, var, pvar, cumpvar),)` (NamedTuple of columns; wrap in `DataFrame` as needed).
+"""
+function Base.summary(object::Plsr, X::Union{AbstractVector, AbstractMatrix})
+    X = dense64(ensure_mat(X))
+    n, a = size(object.T)
+    p = nco(X)
+    xvar = Vector{Float64}(undef, a); pvar = similar(xvar); cumpvar = similar(xvar)
+    rc = ccall((:jcb200_summary, LIB), Cint,
+               (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               X, n, n, p, object.xmeans, object.xscales, object.weights, a == 0 ? C_NULL : object.P,
+               a == 0 ? C_NULL : object.TT, a, xvar, pvar, cumpvar)
+    check(rc, "summary")
+    (explvarx = (nlv = collect(1:a), var = xvar, pvar = pvar, cumpvar = cumpvar),)
+end
+
 # ---------------------------------------------------------------- gridscorelv (src/gridscore.jl:167-221)
 """
     gridscorelv(Xtrain, Ytrain, X, Y; score, nlv, kwargs...)

@@ -182,3 +182,26 @@ def predict(obj, X, *, nlv=None):
                                              k_lo, k_hi, arr)
         _lib.check(rc, "predict")
     return PredResult(preds[0] if nk == 1 else preds)
+
+
+def summary(obj, X):
+    """Base.summary(object::Plsr, X) (:246-260): `(explvarx = table(nlv, var, pvar, cumpvar),)` for the
+    X the model was fitted on; a pandas DataFrame when pandas is importable, else a dict of arrays."""
+    X = _fmat(X)
+    n, a = obj.T.shape
+    p = X.shape[1]
+    if X.shape[0] != n:
+        raise ValueError(f"DimensionMismatch: X has {X.shape[0]} rows, the model was fitted on {n}")
+    xvar, pvar, cum = np.empty(a), np.empty(a), np.empty(a)
+    P = np.asfortranarray(obj.P)
+    rc = _lib.lib().jcb200_summary(_ptr(X), _ld(X), n, p, _ptr(obj.xmeans), _ptr(obj.xscales),
+                                   _ptr(np.ascontiguousarray(obj.weights)), _ptr(P) if a else None,
+                                   _ptr(obj.TT) if a else None, a, _ptr(xvar), _ptr(pvar), _ptr(cum))
+    _lib.check(rc, "summary")
+    out = {"nlv": np.arange(1, a + 1), "var": xvar, "pvar": pvar, "cumpvar": cum}
+    try:
+        import pandas as pd
+        out = pd.DataFrame(out)
+    except Exception:
+        pass
+    return namedtuple("SummaryResult", ["explvarx"])(out)

@@ -194,6 +194,17 @@ def predict(obj, X, *, nlv=None):
     return pred[0] if len(pred) == 1 else pred
 
 
+def summary(obj, X):
+    """plskern.jl:246-260 — explained X-variance table (nlv, var, pvar, cumpvar)."""
+    X = ensure_mat(X)
+    n, nlv = obj.T.shape
+    Xs = cscale(X, obj.xmeans, obj.xscales)
+    sstot = np.sum(obj.weights @ (Xs ** 2))                # :252
+    tt_adj = np.sum(obj.P ** 2, axis=0) * obj.TT           # :254
+    pvar = tt_adj / sstot
+    return {"nlv": np.arange(1, nlv + 1), "var": tt_adj / n, "pvar": pvar, "cumpvar": np.cumsum(pvar)}
+
+
 # ---------------------------------------------------------------- parity aid
 def sign_align(ref, dev):
     """Per-LV signs s_a = sign(<W_ref[:,a], W_dev[:,a]>): columns a

@@ -262,3 +262,18 @@ def test_concurrent_callers(jc):
     for i in range(4):
         assert np.array_equal(out[i][0].T, solo[i].T) and np.array_equal(out[i][0].R, solo[i].R)
         assert np.array_equal(out[i][1], jc.predict(solo[i], probs[i][0][:7]).pred)
+
+
+def test_summary_explained_variance(jc):
+    """Next row (SURVEY 8f-3): Base.summary(::Plsr, X), plskern.jl:246-260."""
+    n, p, q, nlv = 2500, 90, 2, 7
+    X = synth.synth_matrix(1, n, p) * (1 + np.arange(p))[None, :]
+    Y = synth.synth_matrix(2, n, q) + X[:, :q]
+    w = synth.synth_weights(n, uniform=False)
+    for scal in (False, True):
+        fm = jc.plskern(X, Y, w, nlv=nlv, scal=scal)
+        got = jc.summary(fm, X).explvarx
+        ref = oracle.summary(oracle.plskern(X, Y, w, nlv=nlv, scal=scal), X)
+        for col in ("var", "pvar", "cumpvar"):
+            assert relerr(np.asarray(got[col]), ref[col]) < TOL, (scal, col)
+        assert list(got["nlv"]) == list(range(1, nlv + 1))
