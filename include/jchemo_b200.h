@@ -75,6 +75,11 @@ int64_t jcb200_launch_count(void);
 /* Page-lock / unlock a caller's host array so that the copies run at full PCIe speed. */
 int jcb200_host_register(void* ptr, int64_t bytes);
 int jcb200_host_unregister(void* ptr);
+/* Page-locked host memory from a reuse pool, for large caller-owned OUTPUT arrays (the scores T): a copy
+ * into it runs at PCIe speed instead of through the pageable staging path.  Freed blocks are kept (up to
+ * 3 GB) for later calls.  jcb200_host_free may be called from a finalizer thread. */
+void* jcb200_host_alloc(int64_t bytes);
+int jcb200_host_free(void* ptr);
 
 /* ---- host-pointer entry points (the drop-in path) ------------------------------------------- */
 
@@ -138,7 +143,7 @@ int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const dou
  * the single buffer a row-sharded fit all-reduces (sum) across GPUs. */
 int64_t jcb200_packed_len(int64_t p, int64_t q);
 
-/* Strided-sample pivot c (p+q+1 doubles, device): column means of up to 65536 evenly spaced rows of
+/* Strided-sample pivot c (p+q+1 doubles, device): column means of up to 16384 evenly spaced rows of
  * the shard, or all zeros when every column has mean^2 <= 64 variance (centring then costs more
  * FP64-pipe cycles than it saves digits); element p+q is 1.0 when centring is on, 0.0 otherwise.
  * Multi-GPU: rank 0 computes it and broadcasts, so all partial Grams share one pivot. */

@@ -25,6 +25,8 @@ SIGNATURES = {
     "jcb200_launch_count": (i64, []),
     "jcb200_host_register": (C.c_int, [C.c_void_p, i64]),
     "jcb200_host_unregister": (C.c_int, [C.c_void_p]),
+    "jcb200_host_alloc": (C.c_void_p, [i64]),
+    "jcb200_host_free": (C.c_int, [C.c_void_p]),
     "jcb200_plskern_fit": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32,
                                      i32, i32, C.c_void_p, i64] + [C.c_void_p] * 10 +
                            [C.POINTER(i32)]),

@@ -236,6 +236,7 @@ void jcb200_shutdown(void) {
     free_buf(c->hSmall);
     free_buf(c->hPred);
     free_staging(c);
+    pinned_release_all();
     if (c->sched_host) cudaFreeHost(c->sched_host);
     c->sched_host = nullptr;
     c->sched_host_bytes = 0;
@@ -293,6 +294,20 @@ int jcb200_host_register(void* ptr, int64_t bytes) {
     API_PROLOGUE();
     JCB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
     return 0;
+}
+
+void* jcb200_host_alloc(int64_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    tl_error[0] = 0;
+    if (bytes <= 0 || ready_locked() != 0) return nullptr;
+    void* p = pinned_alloc((size_t)bytes);
+    if (!p) set_error("cudaHostAlloc of %lld bytes failed", (long long)bytes);
+    return p;
+}
+
+int jcb200_host_free(void* ptr) {
+    // no API mutex: may run from a garbage-collector finalizer while another thread is inside a call
+    return pinned_free(ptr) == 0 ? 0 : JCB200_EINVAL;
 }
 
 int jcb200_host_unregister(void* ptr) {

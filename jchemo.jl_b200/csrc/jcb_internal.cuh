@@ -93,6 +93,9 @@ int h2d_2d(Ctx* c, double* dDst, int64_t ldd, const double* hSrc, int64_t lds, i
 int d2h_2d(Ctx* c, double* hDst, int64_t ldd, const double* dSrc, int64_t lds, int64_t rows, int64_t cols,
            cudaStream_t st);
 void free_staging(Ctx* c);
+void* pinned_alloc(size_t bytes);
+int pinned_free(void* p);
+void pinned_release_all();
 void phase_end(Ctx* c, int ph);
 
 // ---------------------------------------------------------------- kernel launchers

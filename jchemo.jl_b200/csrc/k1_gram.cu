@@ -34,6 +34,9 @@ namespace jcb {
 #ifndef JCB_KT
 #define JCB_KT 56
 #endif
+#ifndef JCB_K8_BAR
+#define JCB_K8_BAR 0   /* per-SMSP pacing barrier at every k8-step: measured neutral (8.39 vs 8.40 ms), left off */
+#endif
 #ifndef JCB_NSTAGE
 #define JCB_NSTAGE 2
 #endif
@@ -114,7 +117,7 @@ struct GramParams {
 //  * The A operand (rows of G) is used RAW; only the B operand is centred (and weighted):
 //      acc_ij = sum_k x_ki * w_k (x_kj - c_j)  =  G_ij + c_i s_j ,  s_j = sum_k w_k (x_kj - c_j)
 //    K3 subtracts the rank-one term c_i s_j exactly (s is accumulated by the diagonal units); with the
-//    64K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
+//    16K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
 //    compete with DMMA for the FP64 pipe.
 //  * DIAG units skip the 8x8 blocks below the diagonal and accumulate the column sums; NBC < 4 (edge
 //    and Y blocks) skips empty column blocks; MASKED is the zero-filled tail stage of the unweighted
@@ -130,11 +133,18 @@ __device__ __forceinline__ void stage_steps(const double* __restrict__ tA, const
                                             const double* __restrict__ wt, const double (&pB)[4],
                                             double (&acc)[4][4][2], double (&bsum)[4], double& wsum,
                                             const bool sum_w, const int krow0, const int rows_valid,
-                                            Poll& poll) {
+                                            const int bar_id, const int bar_threads, Poll& poll) {
     constexpr int MBC = DIAG ? NBC : 4;
     constexpr int NG = DIAG ? NBC : (NBC >= 2 ? 2 : 1);
 #pragma unroll 1
     for (int k8 = 0; k8 < KT / 8; ++k8) {
+#if JCB_K8_BAR
+        // The warp scheduler favours some warps of an SMSP; left alone they run a full stage ahead, block on
+        // the ring, and leave too few warps to hide the LDS -> DADD -> DMMA latency of the others (measured:
+        // 11 % of the FP64 pipe idle).  A named barrier among the SMSP's active warps at every k8-step keeps
+        // them within one step of each other.
+        if (bar_threads > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+#endif
         poll();
         double2 a[MBC];
 #pragma unroll
@@ -239,6 +249,10 @@ __device__ __noinline__ void producer_issue(Producer& P, const GramParams& prm,
                                             const CUtensorMap* mapW, unsigned char* smem,
                                             uint64_t* full) {
     const int buf = P.issued % NSTAGE;
+#ifdef JCB_K1_TRACE
+    if (prm.trace && (blockIdx.x % 45) == 0 && P.issued < 64)
+        prm.trace[4 * 64 * NCW * 3 + (blockIdx.x / 45) * 64 + P.issued] = clock64();
+#endif
     const uint32_t bytes = P.nranges * 4 * SLOT_DOUBLES * 8 + (WEIGHTED ? KT * 8 : 0);
     mbar_arrive_expect_tx(&full[buf], bytes);
     unsigned char* base = smem + buf * STAGE_BYTES;
@@ -266,7 +280,8 @@ __device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u
                                             const CUtensorMap* mapW, const K1Shared sh, Producer& P,
                                             const bool producer, uint32_t& it, const int g, const int kk,
                                             const double (&pB)[4], double (&acc)[4][4][2],
-                                            double (&bsum)[4], double& wsum) {
+                                            double (&bsum)[4], double& wsum, const int bar_id,
+                                            const int bar_threads) {
     const bool sum_w = (u.sums & 2) != 0;
     const int lane = threadIdx.x & 31;
     const int offA = u.sa * SLOT_DOUBLES + g * KT + 2 * kk;
@@ -307,10 +322,10 @@ __device__ __forceinline__ void run_segment(const SegDesc& seg, const UnitDesc u
         // (0 - c != 0) or counted (sum of weights); without centring they contribute nothing anyway
         if (!WEIGHTED && rows_left < KT && (CENTER || (DIAG && sum_w)))
             stage_steps<WEIGHTED, DIAG, NBC, CENTER, true>(tA, tB, wt, pB, acc, bsum, wsum, sum_w, 2 * kk,
-                                                           (int)rows_left, poll);
+                                                           (int)rows_left, bar_id, bar_threads, poll);
         else
             stage_steps<WEIGHTED, DIAG, NBC, CENTER, false>(tA, tB, wt, pB, acc, bsum, wsum, sum_w,
-                                                            2 * kk, KT, poll);
+                                                            2 * kk, KT, bar_id, bar_threads, poll);
         __syncwarp();
 #ifdef JCB_K1_TRACE
         if (tr) trp[2] = clock64();
@@ -362,6 +377,14 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         const SegDesc seg = prm.segs[sg];
         const GroupDesc* gd = &prm.groups[seg.group];
         const UnitDesc u = gd->unit[warp];
+#if JCB_K8_BAR
+        __syncthreads();   // the pacing barriers of two segments (different thread counts) must not overlap
+#endif
+        // active warps on this warp's SMSP (warp % 4) in this group: they pace each other per k8-step
+        int nact = 0;
+#pragma unroll
+        for (int j = 0; j < NCW / 4; ++j) nact += gd->unit[(warp & 3) + 4 * j].kind != 0;
+        const int bar_id = 1 + (warp & 3), bar_threads = nact * 32;
         double acc[4][4][2];
         double bsum[4], pB[4];
         double wsum = 0.0;
@@ -390,10 +413,10 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     do {                                                                                             \
         if (center)                                                                                  \
             run_segment<WEIGHTED, D, N, true>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, g, \
-                                              kk, pB, acc, bsum, wsum);                              \
+                                              kk, pB, acc, bsum, wsum, bar_id, bar_threads);         \
         else                                                                                         \
             run_segment<WEIGHTED, D, N, false>(seg, u, prm, &mapX, &mapY, &mapW, sh, P, producer, it, \
-                                               g, kk, pB, acc, bsum, wsum);                          \
+                                               g, kk, pB, acc, bsum, wsum, bar_id, bar_threads);     \
     } while (0)
         switch (u.kind ? ((u.kind == 2 ? 4 : 0) + (u.nbc - 1)) : -1) {
             case 0: JCB_SEG(false, 1); break;
@@ -507,7 +530,7 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     }
 }
 
-// Strided-sample pivot: mean of up to 65536 rows per column, taken as 256 evenly spaced chunks of 256
+// Strided-sample pivot: mean of up to 16384 rows per column, taken as 64 evenly spaced chunks of 256
 // consecutive rows (coalesced 2 KB reads).  One block per column.  The pivot only has to be CLOSE to
 // the mean (K3 corrects exactly); a large sample keeps the correction terms c_i s_j and delta delta'
 // far below the rounding level even for offset-heavy data.  ratio[col] = mean^2 / variance of the
@@ -520,7 +543,7 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
     __shared__ double red[16];
     double s = 0.0, s2 = 0.0;
     int64_t cnt;
-    if (n <= 65536) {
+    if (n <= 16384) {
         cnt = n;
         for (int64_t i = threadIdx.x; i < n; i += 256) {
             const double v = src[i];
@@ -528,9 +551,10 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
             s2 += v * v;
         }
     } else {
-        cnt = 65536;
-        const int64_t stride = n / 256;            // chunk c covers rows [c*stride, c*stride + 256)
-        for (int c = 0; c < 256; ++c) {
+        cnt = 16384;
+        const int64_t stride = n / 64;             // chunk c covers rows [c*stride, c*stride + 256)
+#pragma unroll 8
+        for (int c = 0; c < 64; ++c) {
             const double v = src[c * stride + threadIdx.x];
             s += v;
             s2 += v * v;
@@ -839,7 +863,7 @@ extern "C" int jcb200_debug_trace(long long* host, int n) {
     if (!g_trace) return -1;
     cudaDeviceSynchronize();
     cudaMemcpy(host, g_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
-    return 4 * 64 * NCW * 3;
+    return 4 * 64 * NCW * 3 + 256;
 }
 #endif
 
@@ -954,8 +978,8 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
 #ifdef JCB_K1_TRACE
     {
         static long long* tracebuf = nullptr;
-        if (!tracebuf) cudaMalloc(&tracebuf, 4 * 64 * NCW * 3 * sizeof(long long));
-        cudaMemsetAsync(tracebuf, 0, 4 * 64 * NCW * 3 * sizeof(long long), c->stream);
+        if (!tracebuf) cudaMalloc(&tracebuf, (4 * 64 * NCW * 3 + 256) * sizeof(long long));
+        cudaMemsetAsync(tracebuf, 0, (4 * 64 * NCW * 3 + 256) * sizeof(long long), c->stream);
         prm.trace = tracebuf;
         g_trace = tracebuf;
     }

@@ -21,8 +21,15 @@ namespace jcb {
 
 constexpr int XM_MT = 128;        // rows per tile
 constexpr int XM_PITCH = 132;     // shared pitch of a column (doubles)
-constexpr int XM_KC = 32;         // columns of X per stage
-constexpr int XM_MPITCH = 36;     // shared pitch of a row of packed M^T (doubles)
+#ifndef JCB_XM_KC
+#define JCB_XM_KC 32
+#endif
+#ifndef JCB_XM_OCC
+#define JCB_XM_OCC 1
+#endif
+constexpr int XM_KC = JCB_XM_KC;  // columns of X per stage (<= 32: one bulk copy per producer lane)
+constexpr int XM_MPITCH = XM_KC + 4;   // shared pitch of a row of packed M^T (== 4 mod 16: conflict free)
+constexpr int XM_OCC = JCB_XM_OCC;     // CTAs per SM the launch is sized for
 constexpr int XM_NCW = 8;         // consumer warps
 constexpr int XM_THREADS = (XM_NCW + 1) * 32;
 constexpr int XM_MAXNB = 8;       // up to 64 output columns per pass
@@ -69,7 +76,7 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
 }
 
 template <int NPB, int NEX, bool SWEEP>
-__global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams prm) {
+__global__ void __launch_bounds__(XM_THREADS, XM_OCC) xmul_kernel(const XmulParams prm) {
     // NPB column blocks go through DMMA; NEX (<= 2) leftover columns are plain DFMA dot products on the
     // A fragments this lane already holds (a whole padded 8-column block for 1-2 columns would cost
     // 1/NPB more DMMA time: at nlv = 25 the score GEMM drops from 4 to 3 blocks)
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(XM_THREADS, 1) xmul_kernel(const XmulParams pr
                     __syncwarp();
                     const int k = ch * XM_KC + lane;
                     const double* src = k < prm.p ? prm.X + row0 + (int64_t)k * prm.ldx : prm.zeros;
-                    bulk_load(xs + lane * XM_PITCH, src, crow * 8, &full[buf]);
+                    if (lane < XM_KC) bulk_load(xs + lane * XM_PITCH, src, crow * 8, &full[buf]);
                     if (lane == 0) bulk_load(ms, msrc, MBYTES, &full[buf]);
                 } else {
                     // ragged / unaligned tile: plain loads through registers
@@ -264,7 +271,7 @@ static int launch_xmul_t(Ctx* c, XmulParams& prm) {
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
     const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
                       (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
-    int nstage = (int)((220 * 1024 - fixed) / stage);
+    int nstage = (int)(((XM_OCC == 2 ? 110 : 220) * 1024 - fixed) / stage);
     if (nstage > 4) nstage = 4;
     if (nstage < 2) {
         set_error("xmul: p=%d too large for the shared-memory budget", prm.p);
@@ -275,7 +282,7 @@ static int launch_xmul_t(Ctx* c, XmulParams& prm) {
     JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem));
     const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
-    const int grid = (int)std::min<int64_t>(ntiles, c->num_sms);
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)XM_OCC * c->num_sms);
     xmul_kernel<NPB, NEX, SWEEP><<<grid, XM_THREADS, smem, c->stream>>>(prm);
     JCB_LAUNCH_CHECK();
     return 0;

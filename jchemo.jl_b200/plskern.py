@@ -8,6 +8,7 @@ libjchemo_b200.so on the GPU through the C ABI; this file only coerces shapes
 exceptions.  There is no CPU fallback.
 """
 import ctypes as C
+import weakref
 from collections import namedtuple
 from dataclasses import dataclass
 from typing import Optional
@@ -63,6 +64,22 @@ def _fmat(X):
     return X
 
 
+def _out_empty(shape):
+    """Column-major Float64 output array.  Large ones come from the library's page-locked pool
+    (jcb200_host_alloc): the device-to-host copy of the scores then runs at PCIe speed; the block goes
+    back to the pool when the array is garbage collected.  Falls back to ordinary memory."""
+    nbytes = int(np.prod(shape)) * 8
+    if nbytes >= (1 << 22):
+        lib = _lib.lib()
+        p = lib.jcb200_host_alloc(nbytes)
+        if p:
+            buf = (C.c_char * nbytes).from_address(p)
+            arr = np.frombuffer(buf, dtype=np.float64).reshape(shape, order="F")
+            weakref.finalize(buf, lib.jcb200_host_free, C.c_void_p(p))
+            return arr
+    return np.empty(shape, order="F")
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -85,7 +102,7 @@ def _fit(X, Y, weights, nlv, scal, writeback):
             raise ValueError(f"DimensionMismatch: weights has length {w.shape[0]}, X has {n} rows")
     nlv = int(nlv)
     a = max(0, min(n, p, nlv))                                   # plskern.jl:116
-    T = np.empty((n, a), order="F")
+    T = _out_empty((n, a))
     P = np.empty((p, a), order="F")
     R = np.empty((p, a), order="F")
     W = np.empty((p, a), order="F")
@@ -93,7 +110,7 @@ def _fit(X, Y, weights, nlv, scal, writeback):
     TT = np.empty(a)
     xmeans, xscales = np.empty(p), np.empty(p)
     ymeans, yscales = np.empty(q), np.empty(q)
-    w_out = np.empty(n)
+    w_out = _out_empty((n,))
     nlv_out = C.c_int32(0)
     rc = lib.jcb200_plskern_fit(_ptr(X), _ld(X), _ptr(Y), _ld(Y), _ptr(w), n, p, q, nlv,
                                 1 if scal else 0, 1 if writeback else 0, _ptr(T), max(n, 1), _ptr(P),
