@@ -129,6 +129,20 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
                      const double* xscales, const double* ymeans, const double* yscales, int32_t k_lo,
                      int32_t k_hi, double* ssr, double* sumres, double* ysum, double* ysumsq);
 
+/* gridcvlv for fun = plskern, ONE repetition (next row) — /root/reference/src/gridcv.jl:
+ * 187-228: for every segment j the model is fitted on the rows NOT in segment j (uniform weights) and
+ * scored on segment j for nlv = k_lo..k_hi.  perm (n, zero-based) lists the rows segment by segment,
+ * segment j = perm[seg_start[j] : seg_start[j+1]]; rows after seg_start[nseg] are in every training set.
+ * Gram down-dating: one pass over X for all K Grams, then K solves and K scoring passes over the
+ * segments (one more pass in total) instead of K fits on K row-copies.  Outputs as jcb200_gridscore, one
+ * block per segment: ssr, sumres nseg x (nk x q), ysum, ysumsq nseg x q.  k_hi must not exceed
+ * min(p, smallest training set).  reuse_xy != 0 keeps the device copy of X, Y of the previous call with
+ * the same pointers and shape (repetitions of one CV). */
+int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t n, int64_t p,
+                  int64_t q, const int64_t* perm, const int64_t* seg_start, int32_t nseg, int32_t k_lo,
+                  int32_t k_hi, int32_t scal, int32_t reuse_xy, double* ssr, double* sumres, double* ysum,
+                  double* ysumsq);
+
 /* Base.summary(::Plsr, X) (next row) — /root/reference/src/plskern.jl:246-260: explained
  * X-variance per LV.  One pass over X for sstot = sum(weights' * ((X - xmeans)./xscales).^2); then
  * tt_adj = colsum(P.^2) .* TT, pvar = tt_adj / sstot, cumpvar = cumsum(pvar), xvar = tt_adj / n

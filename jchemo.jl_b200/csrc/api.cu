@@ -235,6 +235,11 @@ void jcb200_shutdown(void) {
     free_buf(c->hT);
     free_buf(c->hSmall);
     free_buf(c->hPred);
+    free_buf(c->cvX);
+    free_buf(c->cvY);
+    free_buf(c->cvIdx);
+    free_buf(c->cvPk);
+    c->cv_hostX = c->cv_hostY = nullptr;
     free_staging(c);
     pinned_release_all();
     if (c->sched_host) cudaFreeHost(c->sched_host);
@@ -761,6 +766,151 @@ int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const dou
         cum += pvar[l];
         cumpvar[l] = cum;
         xvar[l] = tta / (double)n;
+    }
+    return 0;
+}
+
+int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t n, int64_t p,
+                  int64_t q, const int64_t* perm, const int64_t* seg_start, int32_t nseg, int32_t k_lo,
+                  int32_t k_hi, int32_t scal, int32_t reuse_xy, double* ssr, double* sumres, double* ysum,
+                  double* ysumsq) {
+    API_PROLOGUE();
+    ARG_CHECK(X && Y && perm && seg_start && ssr && sumres && ysum && ysumsq && n > 1 && p > 0 && q > 0 &&
+                  ldx >= n && ldy >= n && nseg >= 1 && k_lo >= 0 && k_hi >= k_lo,
+              "gridcv: bad argument");
+    ARG_CHECK(seg_start[0] == 0 && seg_start[nseg] <= n, "gridcv: bad segment offsets");
+    int64_t min_train = n;
+    for (int j = 0; j < nseg; ++j) {
+        const int64_t len = seg_start[j + 1] - seg_start[j];
+        ARG_CHECK(len >= 1 && len < n, "gridcv: empty segment or segment covering every row");
+        min_train = std::min(min_train, n - len);
+    }
+    ARG_CHECK(k_hi <= p && k_hi <= min_train, "gridcv: nlv exceeds min(n_train, p)");
+    const int ka = k_hi > 0 ? k_hi : 1;
+    const int nk = k_hi - k_lo + 1;
+    const int nslab = nseg + (seg_start[nseg] < n ? 1 : 0);     // + rows that are in no segment
+    cudaStream_t st = c->stream;
+
+    // ---- row map: slab j starts at an even row of the permuted copy (16-byte aligned columns)
+    std::vector<int64_t> off(nslab + 1), len(nslab);
+    int64_t tot = 0, maxlen = 0;
+    for (int j = 0; j < nslab; ++j) {
+        const int64_t a0 = j < nseg ? seg_start[j] : seg_start[nseg];
+        const int64_t a1 = j < nseg ? seg_start[j + 1] : n;
+        len[j] = a1 - a0;
+        off[j] = tot;
+        tot = even_up(tot + len[j]);
+        maxlen = std::max(maxlen, len[j]);
+    }
+    off[nslab] = tot;
+    const int64_t ldp = even_up(tot);
+    std::vector<int64_t> src_row((size_t)ldp, -1);
+    {
+        std::vector<char> seen((size_t)n, 0);
+        int64_t k = 0;
+        for (int j = 0; j < nslab; ++j)
+            for (int64_t i = 0; i < len[j]; ++i, ++k) {
+                const int64_t r = perm[k];
+                ARG_CHECK(r >= 0 && r < n && !seen[(size_t)r], "gridcv: perm is not a permutation of 0..n-1");
+                seen[(size_t)r] = 1;
+                src_row[(size_t)(off[j] + i)] = r;
+            }
+        ARG_CHECK(k == n, "gridcv: perm does not cover every row");
+    }
+
+    // ---- device copies of X, Y (kept across calls for the repetitions of one CV)
+    const int64_t ld = even_up(n);
+    const bool have = reuse_xy && c->cv_hostX == X && c->cv_hostY == Y && c->cv_n == n && c->cv_p == p &&
+                      c->cv_q == q;
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    JCB_TRY(ensure(c->cvX, (size_t)ldp * p * 8));
+    JCB_TRY(ensure(c->cvY, (size_t)ldp * q * 8));
+    JCB_TRY(ensure(c->cvIdx, (size_t)ldp * 8));
+    JCB_TRY(ensure(c->hT, (size_t)even_up(maxlen) * ka * 8));
+    JCB_TRY(ensure(c->hPred, (size_t)even_up(maxlen) * 2 * q * 8));
+    const int64_t plen = packed_len(p, q), splen = packed_len(ka, 2 * q);
+    JCB_TRY(ensure(c->cvPk, (size_t)((nslab + 2) * plen + (size_t)nseg * (splen + (size_t)q * ka + q)) * 8));
+    const size_t small = (size_t)(p + q + 1) + 3 * (size_t)p * ka + (size_t)q * ka + ka + 2 * (p + q) + 2 +
+                         (ka + 2 * q + 1) + 64;
+    JCB_TRY(ensure(c->hSmall, small * 8));
+    double* dX = (double*)c->hX.p;
+    double* dY = (double*)c->hY.p;
+    double* dXp = (double*)c->cvX.p;
+    double* dYp = (double*)c->cvY.p;
+    int64_t* dIdx = (int64_t*)c->cvIdx.p;
+    double* dT = (double*)c->hT.p;
+    double* dYaug = (double*)c->hPred.p;
+    double* pk = (double*)c->cvPk.p;                 // [nslab] slab Grams | total | train | per-seg score data
+    double* pk_total = pk + (size_t)nslab * plen;
+    double* pk_train = pk_total + plen;
+    double* seg_out = pk_train + plen;
+    Carver cv(c->hSmall.p);
+    double* d_pivot = cv.take(p + q + 1);
+    double* dP = cv.take((size_t)p * ka);
+    double* dR = cv.take((size_t)p * ka);
+    double* dW = cv.take((size_t)p * ka);
+    double* dC = cv.take((size_t)q * ka);
+    double* dTT = cv.take(ka);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dym = cv.take(q);
+    double* dys = cv.take(q);
+    double* dsw = cv.take(2);
+    double* dpv0 = cv.take(ka + 2 * q + 1);
+
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    if (!have) {
+        phase_begin(c, JCB200_T_H2D);
+        JCB_TRY(h2d_2d(c, dX, ld, X, ldx, n, p, st));
+        JCB_TRY(h2d_2d(c, dY, ld, Y, ldy, n, q, st));
+        phase_end(c, JCB200_T_H2D);
+        c->cv_hostX = X;
+        c->cv_hostY = Y;
+        c->cv_n = n;
+        c->cv_p = p;
+        c->cv_q = q;
+    }
+    JCB_CUDA(cudaMemcpyAsync(dIdx, src_row.data(), (size_t)ldp * 8, cudaMemcpyHostToDevice, st));
+    JCB_TRY(launch_gather_rows(c, dX, ld, dXp, ldp, dIdx, ldp, p));
+    JCB_TRY(launch_gather_rows(c, dY, ld, dYp, ldp, dIdx, ldp, q));
+    JCB_CUDA(cudaStreamSynchronize(st));             // src_row (host vector) has been consumed
+    JCB_TRY(launch_pivot(c, dX, ld, dY, ld, n, p, q, d_pivot));
+    // ---- one Gram per slab (one pass over X in total), all about the same pivot
+    for (int j = 0; j < nslab; ++j) {
+        JCB_TRY(launch_gram(c, dXp + off[j], ldp, dYp + off[j], ldp, nullptr, len[j], p, q, d_pivot,
+                            pk + (size_t)j * plen, 0));
+        JCB_TRY(launch_packed_add(c, pk_total, pk + (size_t)j * plen, plen, j == 0));
+    }
+    // ---- per segment: down-date, solve, score its own slab
+    std::vector<double> hout((size_t)nseg * (splen + (size_t)q * ka + q));
+    for (int j = 0; j < nseg; ++j) {
+        JCB_TRY(launch_packed_sub(c, pk_total, pk + (size_t)j * plen, pk_train, plen));
+        JCB_TRY(launch_solve(c, pk_train, d_pivot, p, q, k_hi, scal, dP, dR, dW, dC, dTT, dxm, dxs, dym, dys,
+                             dsw));
+        if (k_hi > 0) {
+            JCB_TRY(launch_xmul(c, dXp + off[j], ldp, len[j], p, dxm, dxs, dR, p, k_hi, nullptr, dT,
+                                even_up(maxlen)));
+        } else {
+            JCB_CUDA(cudaMemsetAsync(dT, 0, (size_t)even_up(maxlen) * 8, st));
+        }
+        double* so = seg_out + (size_t)j * (splen + (size_t)q * ka + q);
+        JCB_TRY(launch_gridscore_gram(c, dYp + off[j], ldp, dT, even_up(maxlen), dC, dys, dym, len[j], (int)q,
+                                      k_hi, ka, dYaug, even_up(maxlen), dpv0, so));
+        if (k_hi > 0)
+            JCB_CUDA(cudaMemcpyAsync(so + splen, dC, (size_t)q * k_hi * 8, cudaMemcpyDeviceToDevice, st));
+        JCB_CUDA(cudaMemcpyAsync(so + splen + (size_t)q * ka, dys, (size_t)q * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(hout.data(), seg_out, hout.size() * 8, cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    for (int j = 0; j < nseg; ++j) {
+        const double* so = hout.data() + (size_t)j * (splen + (size_t)q * ka + q);
+        gridscore_from_packed(so, ka, (int)q, k_lo, k_hi, so + splen, so + splen + (size_t)q * ka,
+                              ssr + (size_t)j * nk * q, sumres + (size_t)j * nk * q, ysum + (size_t)j * q,
+                              ysumsq + (size_t)j * q);
     }
     return 0;
 }

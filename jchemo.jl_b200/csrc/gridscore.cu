@@ -101,3 +101,58 @@ void gridscore_from_packed(const double* pk, int ka, int q, int k_lo, int k_hi, 
 }
 
 }  // namespace jcb
+
+// =============================================================================================
+// gridcvlv by Gram down-dating — /root/reference/src/gridcv.jl:187-228 for
+// fun = plskern: for every segment s of a repetition the reference fits on rmrow(X, s) and scores on
+// X[s, :] — K fits and K row-copies of X.  Every quantity a fit needs is a sum over rows, so
+//   Gram(training rows of segment j) = Gram(all rows) - Gram(rows of segment j):
+// the rows are permuted once so that each segment is a contiguous slab, K1 runs once per slab (one pass
+// over X in total, all slabs about the same pivot), and per segment only K3/K4 (solve) and one scoring
+// pass over its own slab remain.
+namespace jcb {
+
+// dst row r of every column = src row src_row[r] (gap rows: -1 -> 0)
+__global__ void gather_rows_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst,
+                                   int64_t ldd, const int64_t* __restrict__ src_row, int64_t nrows) {
+    const int64_t j = blockIdx.y;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = src_row[r];
+        dst[r + j * ldd] = s >= 0 ? src[s + j * lds] : 0.0;
+    }
+}
+
+// out = a - b (packed buffers), and acc += b
+__global__ void packed_sub_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                  double* __restrict__ out, int64_t len) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a[i] - b[i];
+}
+__global__ void packed_add_kernel(double* __restrict__ acc, const double* __restrict__ b, int64_t len,
+                                  int first) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x)
+        acc[i] = (first ? 0.0 : acc[i]) + b[i];
+}
+
+int launch_gather_rows(Ctx* c, const double* src, int64_t lds, double* dst, int64_t ldd,
+                       const int64_t* d_src_row, int64_t nrows, int64_t ncols) {
+    dim3 grid((unsigned)std::min<int64_t>((nrows + 255) / 256, 256), (unsigned)ncols);
+    gather_rows_kernel<<<grid, 256, 0, c->stream>>>(src, lds, dst, ldd, d_src_row, nrows);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_packed_sub(Ctx* c, const double* a, const double* b, double* out, int64_t len) {
+    packed_sub_kernel<<<(int)std::min<int64_t>((len + 255) / 256, 1184), 256, 0, c->stream>>>(a, b, out, len);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_packed_add(Ctx* c, double* acc, const double* b, int64_t len, int first) {
+    packed_add_kernel<<<(int)std::min<int64_t>((len + 255) / 256, 1184), 256, 0, c->stream>>>(acc, b, len, first);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace jcb

@@ -69,6 +69,10 @@ struct Ctx {
     Buf xmul_ws;
     // general scratch for the host-pointer API
     Buf hX, hY, hW, hT, hSmall, hPred;
+    Buf cvX, cvY, cvIdx, cvPk;      // gridcv: permuted copies, row map, per-segment packed buffers
+    const void* cv_hostX = nullptr; // host pointers / shape of the copy resident in hX, hY (reuse_xy)
+    const void* cv_hostY = nullptr;
+    int64_t cv_n = 0, cv_p = 0, cv_q = 0;
     // per-launch K1 timing ring (bench.py's roofline: average K1 duration over the timed region)
     static constexpr int GRAM_RING = 256;
     cudaEvent_t gram_ev0[GRAM_RING], gram_ev1[GRAM_RING];
@@ -129,6 +133,10 @@ int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmean
 int launch_gridscore_gram(Ctx* c, const double* dY, int64_t ldy, const double* dT, int64_t ldt,
                           const double* dC, const double* dys, const double* dymeans, int64_t m, int q,
                           int k_hi, int ka, double* dYaug, int64_t lda, double* d_pivot0, double* d_packed);
+int launch_gather_rows(Ctx* c, const double* src, int64_t lds, double* dst, int64_t ldd,
+                       const int64_t* d_src_row, int64_t nrows, int64_t ncols);
+int launch_packed_sub(Ctx* c, const double* a, const double* b, double* out, int64_t len);
+int launch_packed_add(Ctx* c, double* acc, const double* b, int64_t len, int first);
 void gridscore_from_packed(const double* pk, int ka, int q, int k_lo, int k_hi, const double* C,
                            const double* ys, double* ssr, double* sumres, double* ysum, double* ysumsq);
 

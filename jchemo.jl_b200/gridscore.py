@@ -82,3 +82,61 @@ def gridscorelv(Xtrain, Ytrain, X, Y, *, score, nlv, fun=plskern, **kwargs):
         return pd.DataFrame(out)
     except Exception:
         return out
+
+
+def gridcvlv(X, Y, *, segm, score, nlv, fun=plskern, scal=False):
+    """gridcvlv(X, Y; segm, score, fun = plskern, nlv) -> (res, res_rep), reference
+    `/root/reference/src/gridcv.jl:187-228` (branch `pars === nothing`).  `segm` is a list of repetitions,
+    each a list of zero-based row-index arrays (the segments; disjoint within a repetition, as `segmkf` /
+    `segmts` build them).  Every repetition is ONE call of `jcb200_gridcv`: Gram down-dating on the GPU
+    instead of K fits on K row-copies (next row)."""
+    if fun is not plskern:
+        raise TypeError("the fused path covers fun = plskern")
+    name = score if isinstance(score, str) else getattr(score, "__name__", None)
+    if name not in SCORES:
+        raise ValueError(f"score must be one of {SCORES}")
+    X, Y = _fmat(X), _fmat(Y)
+    n, p = X.shape
+    q = Y.shape[1]
+    if Y.shape[0] != n:
+        raise ValueError(f"DimensionMismatch: X has {n} rows, Y has {Y.shape[0]}")
+    ks = np.atleast_1d(np.asarray(nlv))
+    lo, hi = max(0, int(ks.min())), min(p, int(ks.max()))                    # gridcv.jl:193
+    nk = hi - lo + 1
+    lib = _lib.lib()
+    rows = []
+    for i, listsegm in enumerate(segm):
+        segs = [np.asarray(s, dtype=np.int64).reshape(-1) for s in listsegm]
+        allidx = np.concatenate(segs)
+        if np.unique(allidx).size != allidx.size:
+            raise ValueError("segments of a repetition must be disjoint")
+        rest = np.setdiff1d(np.arange(n, dtype=np.int64), allidx, assume_unique=True)
+        perm = np.ascontiguousarray(np.concatenate([allidx, rest]))
+        seg_start = np.ascontiguousarray(np.concatenate([[0], np.cumsum([s.size for s in segs])]).astype(np.int64))
+        K = len(segs)
+        ssr = np.empty((K, q, nk))           # per segment: nk x q column-major
+        sres = np.empty((K, q, nk))
+        ysum, ysumsq = np.empty((K, q)), np.empty((K, q))
+        rc = lib.jcb200_gridcv(_ptr(X), _ld(X), _ptr(Y), _ld(Y), n, p, q, _ptr(perm), _ptr(seg_start), K, lo,
+                               hi, 1 if scal else 0, 1 if i > 0 else 0, _ptr(ssr), _ptr(sres), _ptr(ysum),
+                               _ptr(ysumsq))
+        _lib.check(rc, "gridcvlv")
+        for j in range(K):
+            tab = score_table(name, ssr[j].T, sres[j].T, ysum[j], ysumsq[j], segs[j].size)
+            for t in range(nk):
+                rows.append([i + 1, j + 1, lo + t] + list(tab[t]))
+    arr = np.array(rows, dtype=float)
+    res_rep = {"repl": arr[:, 0].astype(int), "segm": arr[:, 1].astype(int), "nlv": arr[:, 2].astype(int)}
+    for c in range(q):
+        res_rep[f"y{c + 1}"] = arr[:, 3 + c]
+    kk = np.unique(res_rep["nlv"])
+    res = {"nlv": kk}
+    for c in range(q):
+        res[f"y{c + 1}"] = np.array([arr[res_rep["nlv"] == k, 3 + c].mean() for k in kk])
+    try:
+        import pandas as pd
+        res, res_rep = pd.DataFrame(res), pd.DataFrame(res_rep)
+    except Exception:
+        pass
+    from collections import namedtuple
+    return namedtuple("GridcvResult", ["res", "res_rep"])(res, res_rep)

@@ -64,3 +64,34 @@ def gridscorelv(Xtrain, Ytrain, X, Y, *, score, nlv, fun=plskern, **kwargs):
     for j in range(res.shape[1]):
         out[f"y{j + 1}"] = res[:, j]
     return out
+
+
+def rmrow(X, s):
+    """utility.jl rmrow: X without the rows s."""
+    keep = np.ones(X.shape[0], dtype=bool)
+    keep[np.asarray(s)] = False
+    return X[keep]
+
+
+def gridcvlv(X, Y, *, segm, score, nlv, fun=plskern, **kwargs):
+    """gridcv.jl:187-228 (pars === nothing): for every repetition i and segment s, gridscorelv on
+    (rmrow(X, s), rmrow(Y, s)) -> (X[s, :], Y[s, :]); `res_rep` has one row per (repl, segm, nlv), `res`
+    is the mean over repetitions and segments per nlv.  Indices are zero-based here."""
+    X, Y = ensure_mat(X), ensure_mat(Y)
+    q = Y.shape[1]
+    rows = []
+    for i, listsegm in enumerate(segm):
+        for j, s in enumerate(listsegm):
+            s = np.asarray(s)
+            z = gridscorelv(rmrow(X, s), rmrow(Y, s), X[s], Y[s], score=score, nlv=nlv, fun=fun, **kwargs)
+            for t in range(len(z["nlv"])):
+                rows.append([i + 1, j + 1, z["nlv"][t]] + [z[f"y{c + 1}"][t] for c in range(q)])
+    arr = np.array(rows, dtype=float)
+    res_rep = {"repl": arr[:, 0].astype(int), "segm": arr[:, 1].astype(int), "nlv": arr[:, 2].astype(int)}
+    for c in range(q):
+        res_rep[f"y{c + 1}"] = arr[:, 3 + c]
+    ks = np.unique(res_rep["nlv"])
+    res = {"nlv": ks}
+    for c in range(q):
+        res[f"y{c + 1}"] = np.array([arr[res_rep["nlv"] == k, 3 + c].mean() for k in ks])
+    return res, res_rep

@@ -277,3 +277,25 @@ def test_summary_explained_variance(jc):
         for col in ("var", "pvar", "cumpvar"):
             assert relerr(np.asarray(got[col]), ref[col]) < TOL, (scal, col)
         assert list(got["nlv"]) == list(range(1, nlv + 1))
+
+
+@pytest.mark.parametrize("scal", [False, True])
+def test_gridcvlv_gram_downdating(jc, scal):
+    """Next row: gridcvlv for fun = plskern by Gram down-dating (one pass over X for all
+    folds) against the oracle's K fits on K row-copies (gridcv.jl:187-228).  Two repetitions: a shuffled
+    3-fold partition (segmkf-like, odd fold sizes) and a single test set (segmts-like)."""
+    n, p, q, nlv = 1501, 60, 2, 8
+    X = synth.synth_matrix(1, n, p) * (1.0 + np.arange(p) / p)[None, :]
+    Y = synth.synth_matrix(2, n, q) + X[:, :q] * 1.5
+    rng = np.random.default_rng(3)
+    idx = rng.permutation(n)
+    segm = [[np.sort(idx[0:500]), np.sort(idx[500:1001]), np.sort(idx[1001:])],
+            [np.sort(rng.permutation(n)[:333])]]
+    got = jc.gridcvlv(X, Y, segm=segm, score="rmsep", nlv=range(0, nlv + 1), scal=scal)
+    ref_res, ref_rep = oracle.gridcvlv(X, Y, segm=segm, score="rmsep", nlv=range(0, nlv + 1), scal=scal)
+    g_rep, g_res = got.res_rep, got.res
+    assert list(g_rep["repl"]) == list(ref_rep["repl"]) and list(g_rep["segm"]) == list(ref_rep["segm"])
+    assert list(g_rep["nlv"]) == list(ref_rep["nlv"])
+    for c in ("y1", "y2"):
+        assert relerr(np.asarray(g_rep[c]), ref_rep[c]) < TOL, c
+        assert relerr(np.asarray(g_res[c]), ref_res[c]) < TOL, c
