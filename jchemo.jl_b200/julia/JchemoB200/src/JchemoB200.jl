@@ -17,7 +17,7 @@ module JchemoB200
 using LinearAlgebra
 using Libdl
 
-export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv
+export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv
 
 const LIB = get(ENV, "JCHEMO_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
@@ -220,6 +220,55 @@ function gridscorelv(Xtrain, Ytrain, X, Y; score::Symbol, nlv, kwargs...)
           error("score must be one of :msep, :rmsep, :ssr, :bias, :sep, :r2, :rpd")
     cols = (; nlv = collect(lo:hi), (Symbol("y", j) => res[:, j] for j in 1:q)...)
     cols
+end
+
+# ---------------------------------------------------------------- gridcvlv (src/gridcv.jl:187-228)
+"""
+    gridcvlv(X, Y; segm, score, nlv, scal = false)
+
+`Jchemo.gridcvlv` for `fun = plskern` (branch `pars === nothing`).  `segm` as built by `segmkf` / `segmts`
+(a vector of repetitions, each a vector of 1-based row-index vectors, disjoint within a repetition).
+Every repetition is one `jcb200_gridcv` call: Gram down-dating on the GPU instead of K fits on K
+row-copies.  Returns `(res = ..., res_rep = ...)` as NamedTuples of columns.
+"""
+function gridcvlv(X, Y; segm, score::Symbol, nlv, scal = false)
+    X = dense64(ensure_mat(X)); Y = dense64(ensure_mat(Y))
+    n, p = size(X); q = nco(Y)
+    lo = max(0, minimum(nlv)); hi = min(p, maximum(nlv)); nk = hi - lo + 1      # :193
+    repl = Int[]; sg = Int[]; ks = Int[]; ys = [Float64[] for _ in 1:q]
+    for (i, listsegm) in enumerate(segm)
+        K = length(listsegm)
+        allidx = reduce(vcat, listsegm)
+        rest = setdiff(1:n, allidx)
+        perm = Int64.(vcat(allidx, rest)) .- 1
+        seg_start = Int64.(vcat(0, cumsum(length.(listsegm))))
+        ssr = Array{Float64}(undef, nk, q, K); sres = similar(ssr)
+        ysum = Matrix{Float64}(undef, q, K); ysumsq = similar(ysum)
+        rc = ccall((:jcb200_gridcv, LIB), Cint,
+                   (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64},
+                    Int32, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   X, n, Y, n, n, p, q, perm, seg_start, K, lo, hi, scal, i > 1, ssr, sres, ysum, ysumsq)
+        check(rc, "gridcvlv")
+        for j in 1:K
+            m = length(listsegm[j])
+            ms = ssr[:, :, j] ./ m; bi = -sres[:, :, j] ./ m
+            vary = (ysumsq[:, j] ./ m .- (ysum[:, j] ./ m) .^ 2)'
+            tab = score === :msep ? ms : score === :rmsep ? sqrt.(ms) : score === :ssr ? ssr[:, :, j] :
+                  score === :bias ? bi : score === :sep ? sqrt.(ms .- bi .^ 2) :
+                  score === :r2 ? 1 .- ms ./ vary : score === :rpd ? sqrt.(vary) ./ sqrt.(ms) :
+                  error("score must be one of :msep, :rmsep, :ssr, :bias, :sep, :r2, :rpd")
+            for t in 1:nk
+                push!(repl, i); push!(sg, j); push!(ks, lo + t - 1)
+                for c in 1:q
+                    push!(ys[c], tab[t, c])
+                end
+            end
+        end
+    end
+    res_rep = (; repl = repl, segm = sg, nlv = ks, (Symbol("y", c) => ys[c] for c in 1:q)...)
+    uk = sort(unique(ks))
+    res = (; nlv = uk, (Symbol("y", c) => [sum(ys[c][ks .== k]) / count(ks .== k) for k in uk] for c in 1:q)...)
+    (res = res, res_rep = res_rep)
 end
 
 end # module
