@@ -13,14 +13,14 @@
 // exact staged layout, one bulk copy per stage.  8 consumer warps own 16 rows each; centring happens
 // on the fragments.  Results are staged through shared memory so global stores are 128-byte rows.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "jcb_internal.cuh"
 
 namespace jcb {
 
-constexpr int XM_MT = 128;        // rows per tile
-constexpr int XM_PITCH = 132;     // shared pitch of a column (doubles)
+// rows per tile = 16 per consumer warp; shared pitch of a column = rows + 4 (== 4 mod 16: conflict free)
 #ifndef JCB_XM_KC
 #define JCB_XM_KC 32
 #endif
@@ -30,8 +30,8 @@ constexpr int XM_PITCH = 132;     // shared pitch of a column (doubles)
 constexpr int XM_KC = JCB_XM_KC;  // columns of X per stage (<= 32: one bulk copy per producer lane)
 constexpr int XM_MPITCH = XM_KC + 4;   // shared pitch of a row of packed M^T (== 4 mod 16: conflict free)
 constexpr int XM_OCC = JCB_XM_OCC;     // CTAs per SM the launch is sized for
-constexpr int XM_NCW = 8;         // consumer warps
-constexpr int XM_THREADS = (XM_NCW + 1) * 32;
+// consumer warps per CTA: 8 (128-row tiles) or 16 (256-row tiles, 2 KB column segments, 4 warps per SMSP:
+// the kernel is latency bound with 2) — template parameter NCW
 constexpr int XM_MAXNB = 8;       // up to 64 output columns per pass
 
 struct XmulParams {
@@ -75,8 +75,12 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
         mu_pad[k] = k < p ? mu[k] : 0.0;
 }
 
-template <int NPB, int NEX, bool SWEEP>
-__global__ void __launch_bounds__(XM_THREADS, XM_OCC) xmul_kernel(const XmulParams prm) {
+template <int NPB, int NEX, bool SWEEP, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const XmulParams prm) {
+    constexpr int XM_NCW = NCW;
+    constexpr int XM_MT = 16 * NCW;
+    constexpr int XM_PITCH = XM_MT + 4;
+    constexpr int XM_THREADS = (NCW + 1) * 32;
     // NPB column blocks go through DMMA; NEX (<= 2) leftover columns are plain DFMA dot products on the
     // A fragments this lane already holds (a whole padded 8-column block for 1-2 columns would cost
     // 1/NPB more DMMA time: at nlv = 25 the score GEMM drops from 4 to 3 blocks)
@@ -265,27 +269,48 @@ __global__ void sweep_cy_kernel(const double* __restrict__ C, const double* __re
     Cy[e] = C[j + (int64_t)k * q] * ys[j];
 }
 
-template <int NPB, int NEX, bool SWEEP>
-static int launch_xmul_t(Ctx* c, XmulParams& prm) {
+template <int NPB, int NEX, bool SWEEP, int NCW>
+static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     constexpr int NP = NPB * 8 + NEX;
+    constexpr int XM_MT = 16 * NCW;
+    constexpr int XM_PITCH = XM_MT + 4;
+    constexpr int XM_THREADS = (NCW + 1) * 32;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
     const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
                       (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
     int nstage = (int)(((XM_OCC == 2 ? 110 : 220) * 1024 - fixed) / stage);
     if (nstage > 4) nstage = 4;
     if (nstage < 2) {
+        if (NCW == 16) return -1000;                // wide tile does not fit: caller falls back to NCW = 8
         set_error("xmul: p=%d too large for the shared-memory budget", prm.p);
         return JCB200_EINVAL;
     }
     prm.nstage = nstage;
     const int smem = nstage * stage + fixed;
-    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem));
     const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)XM_OCC * c->num_sms);
-    xmul_kernel<NPB, NEX, SWEEP><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+    xmul_kernel<NPB, NEX, SWEEP, NCW><<<grid, XM_THREADS, smem, c->stream>>>(prm);
     JCB_LAUNCH_CHECK();
     return 0;
+}
+
+// 256-row tiles (16 consumer warps) for narrow outputs without the sweep epilogue, else 128-row tiles
+template <int NPB, int NEX, bool SWEEP>
+static int launch_xmul_t(Ctx* c, XmulParams& prm) {
+    if constexpr (!SWEEP && NPB <= 4) {
+        static int wide = -1;
+        if (wide < 0) {
+            const char* e = getenv("JCB_XM_WIDE");
+            wide = e ? atoi(e) : 1;
+        }
+        if (wide && prm.m >= 256 * 148) {
+            const int r = launch_xmul_w<NPB, NEX, SWEEP, 16>(c, prm);
+            if (r != -1000) return r;
+        }
+    }
+    return launch_xmul_w<NPB, NEX, SWEEP, 8>(c, prm);
 }
 
 template <bool SWEEP, int NEX>
