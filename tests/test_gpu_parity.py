@@ -299,3 +299,19 @@ def test_gridcvlv_gram_downdating(jc, scal):
     for c in ("y1", "y2"):
         assert relerr(np.asarray(g_rep[c]), ref_rep[c]) < TOL, c
         assert relerr(np.asarray(g_res[c]), ref_res[c]) < TOL, c
+
+
+def test_empty_new_data(jc):
+    """Zero rows of new data: empty results of the right shape, no device call needed."""
+    X = synth.synth_matrix(1, 80, 6)
+    Y = synth.synth_matrix(2, 80, 2)
+    fm = jc.plskern(X, Y, nlv=3)
+    E = np.empty((0, 6), order="F")
+    assert jc.transform(fm, E).shape == (0, 3)
+    assert jc.predict(fm, E).pred.shape == (0, 2)
+    pr = jc.predict(fm, E, nlv=range(0, 4)).pred
+    assert len(pr) == 4 and all(z.shape == (0, 2) for z in pr)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        jc.predict(fm, np.zeros((3, 5)))
+    with pytest.raises(jc.JchemoB200Error):
+        jc.plskern(np.empty((0, 6), order="F"), np.empty((0, 2), order="F"), nlv=1)     # n = 0 is rejected
