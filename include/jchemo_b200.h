@@ -58,6 +58,15 @@ int jcb200_version(void);
 const char* jcb200_last_error(void);
 /* Bind the library to CUDA device `device` (default 0 on first use). Idempotent. */
 int jcb200_init(int device);
+/* Single-process multi-GPU: bind the library to `ngpu` (1..8) peer-accessible devices of one box.  The
+ * host-pointer fit then shards X, Y, w by contiguous row blocks over them: every device streams its rows
+ * over its own PCIe link and builds its partial Gram; the one exchange of the path is a sum
+ * of the packed partial Grams that every device reads straight out of its peers' memory over NVLink (no
+ * collective library, fixed order, bit-identical on all devices); K3/K4 run redundantly, K5 per shard.
+ * transform / predict / gridscore keep using device_ids[0]. */
+int jcb200_init_multi(int ngpu, const int* device_ids);
+/* Number of devices the library is bound to (0 before initialisation). */
+int jcb200_device_count(void);
 void jcb200_shutdown(void);
 /* external != 0: launch on the caller's stream `cuda_stream` (a cudaStream_t; 0 is the legacy default
  * stream, e.g. torch's current stream); external == 0: back to the library's own stream. */

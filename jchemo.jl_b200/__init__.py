@@ -12,3 +12,12 @@ from .gridscore import gridscorelv, gridcvlv, residual_sums  # noqa: F401
 
 __all__ = ["gridscorelv", "gridcvlv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "ensure_mat",
            "JchemoB200Error", "lib", "last_timings"]
+
+
+def init_multi(device_ids):
+    """Bind the library to several GPUs of one box (single process): the host-pointer fit then shards
+    the rows over them (jcb200_init_multi).  Call before any other entry point."""
+    import ctypes as C
+    ids = (C.c_int * len(device_ids))(*device_ids)
+    from ._lib import check
+    check(lib().jcb200_init_multi(len(device_ids), ids), "init_multi")

@@ -17,6 +17,8 @@ SIGNATURES = {
     "jcb200_version": (C.c_int, []),
     "jcb200_last_error": (C.c_char_p, []),
     "jcb200_init": (C.c_int, [C.c_int]),
+    "jcb200_init_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "jcb200_device_count": (C.c_int, []),
     "jcb200_shutdown": (None, []),
     "jcb200_set_stream": (C.c_int, [C.c_void_p, i32]),
     "jcb200_last_timings": (C.c_int, [c_dp, C.c_int]),

@@ -80,16 +80,10 @@ static void phases_collect(Ctx* c) {
     }
 }
 
-static int init_locked(int device) {
-    Ctx* c = &g_ctx;
-    if (c->ready && c->device == device) {
-        cudaSetDevice(device);
-        return 0;
-    }
-    if (c->ready) {
-        set_error("already initialised on device %d; call jcb200_shutdown first", c->device);
-        return JCB200_EINVAL;
-    }
+static Ctx g_extra[7];        // devices 1..ndev-1 of a single-process multi-GPU set (jcb200_init_multi)
+static int g_ndev = 1;
+
+static int init_ctx(Ctx* c, int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -122,6 +116,8 @@ static int init_locked(int device) {
         c->last_ms[i] = 0.0;
     }
     for (int i = 0; i < 3; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->mg_ev[i], cudaEventDisableTiming));
+    c->k1_attr_set = false;
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
         JCB_CUDA(cudaEventCreate(&c->gram_ev0[i]));
         JCB_CUDA(cudaEventCreate(&c->gram_ev1[i]));
@@ -129,6 +125,19 @@ static int init_locked(int device) {
     c->gram_calls = 0;
     c->ready = true;
     return 0;
+}
+
+static int init_locked(int device) {
+    Ctx* c = &g_ctx;
+    if (c->ready && c->device == device) {
+        cudaSetDevice(device);
+        return 0;
+    }
+    if (c->ready) {
+        set_error("already initialised on device %d; call jcb200_shutdown first", c->device);
+        return JCB200_EINVAL;
+    }
+    return init_ctx(c, device);
 }
 
 static int ready_locked() {
@@ -184,6 +193,177 @@ static int fit_dev_locked(Ctx* c, double* dX, int64_t ldx, double* dY, int64_t l
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ multi-GPU
+// Single-process row sharding over the devices of jcb200_init_multi: device d owns the
+// contiguous row block d; each runs pivot-sharing K1 on its rows while its own PCIe link streams them in;
+// the only exchange is the packed partial Gram, and it is done WITHOUT a collective library: every device
+// sums all peers' packed buffers straight out of peer memory over NVLink (one small kernel, fixed order
+// 0..ndev-1, so every device holds bit-identical sums), then runs K3/K4 redundantly and K5 on its rows.
+__global__ void peer_reduce_kernel(double* __restrict__ out, const double* const* __restrict__ srcs,
+                                   int nsrc, int64_t len) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int d = 0; d < nsrc; ++d) s += srcs[d][i];
+        out[i] = s;
+    }
+}
+
+static Ctx* dev_ctx(int d) { return d == 0 ? &g_ctx : &g_extra[d - 1]; }
+
+static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, const double* w, int64_t n,
+                            int64_t p, int64_t q, int nlv, int scal, int writeback, double* T, int64_t ldt,
+                            double* P, double* R, double* W, double* C, double* TT, double* xmeans,
+                            double* xscales, double* ymeans, double* yscales, double* w_out) {
+    const int nd = g_ndev;
+    const int64_t plen = packed_len(p, q);
+    int64_t per = (n + nd - 1) / nd;
+    per = (per + 1) & ~(int64_t)1;
+    struct Shard {
+        int64_t r0, nr, ld;
+        double *dX, *dY, *dw, *dwout, *dT, *d_part, *d_packed, *d_pivot, *d_sumw, *dP, *dR, *dW, *dC, *dTT,
+            *dxm, *dxs, *dym, *dys;
+        const double** d_srcs;
+    } sh[8];
+    // ---- buffers on every device
+    for (int d = 0; d < nd; ++d) {
+        Ctx* c = dev_ctx(d);
+        JCB_CUDA(cudaSetDevice(c->device));
+        Shard& s = sh[d];
+        s.r0 = std::min(n, (int64_t)d * per);
+        s.nr = std::min(per, n - s.r0);
+        s.ld = even_up(std::max<int64_t>(s.nr, 2));
+        JCB_TRY(ensure(c->hX, (size_t)s.ld * p * 8));
+        JCB_TRY(ensure(c->hY, (size_t)s.ld * q * 8));
+        JCB_TRY(ensure(c->hW, (size_t)s.ld * 2 * 8));
+        JCB_TRY(ensure(c->hT, (size_t)s.ld * (nlv > 0 ? nlv : 1) * 8));
+        const size_t small = 2 * (size_t)plen + (p + q + 1) + 16 + 3 * (size_t)p * nlv + (size_t)q * nlv + nlv +
+                             2 * (p + q) + 64 + 16;
+        JCB_TRY(ensure(c->hSmall, small * 8));
+        s.dX = (double*)c->hX.p;
+        s.dY = (double*)c->hY.p;
+        s.dw = w ? (double*)c->hW.p : nullptr;
+        s.dwout = (double*)c->hW.p + s.ld;
+        s.dT = (double*)c->hT.p;
+        Carver cv(c->hSmall.p);
+        s.d_part = cv.take(plen);
+        s.d_packed = cv.take(plen);
+        s.d_pivot = cv.take(p + q + 1);
+        s.d_sumw = cv.take(2);
+        s.dP = cv.take((size_t)p * nlv);
+        s.dR = cv.take((size_t)p * nlv);
+        s.dW = cv.take((size_t)p * nlv);
+        s.dC = cv.take((size_t)q * nlv);
+        s.dTT = cv.take(nlv);
+        s.dxm = cv.take(p);
+        s.dxs = cv.take(p);
+        s.dym = cv.take(q);
+        s.dys = cv.take(q);
+        s.d_srcs = (const double**)cv.take(8);
+    }
+    // peer pointer tables
+    for (int d = 0; d < nd; ++d) {
+        Ctx* c = dev_ctx(d);
+        JCB_CUDA(cudaSetDevice(c->device));
+        const double* srcs[8];
+        for (int e = 0; e < nd; ++e) srcs[e] = sh[e].d_part;
+        JCB_CUDA(cudaMemcpyAsync(sh[d].d_srcs, srcs, sizeof(double*) * nd, cudaMemcpyHostToDevice, c->stream));
+    }
+    Ctx* c0 = dev_ctx(0);
+    phases_reset(c0);
+    JCB_CUDA(cudaSetDevice(c0->device));
+    phase_begin(c0, JCB200_T_TOTAL);
+    // ---- every device: stream its rows in (its own PCIe link) with K1 on the chunks underneath
+    for (int d = 0; d < nd; ++d) {
+        Ctx* c = dev_ctx(d);
+        Shard& s = sh[d];
+        JCB_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream, cs = c->copy_stream;
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));
+        JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
+        if (d > 0) {
+            // the pivot comes from device 0's first chunk (its copies are already queued): peer copy
+            JCB_CUDA(cudaStreamWaitEvent(st, c0->mg_ev[1], 0));
+            JCB_CUDA(cudaMemcpyPeerAsync(s.d_pivot, c->device, sh[0].d_pivot, c0->device, (p + q + 1) * 8, st));
+        }
+        if (s.nr <= 0) {
+            JCB_CUDA(cudaMemsetAsync(s.d_part, 0, plen * 8, st));
+        } else {
+            if (w) JCB_TRY(h2d_2d(c, s.dw, s.ld, w + s.r0, n, s.nr, 1, cs));
+            int64_t chunk = s.nr;
+            if (s.nr >= 200000) chunk = (((s.nr + 3) / 4) + 1) & ~(int64_t)1;
+            const int nch = (int)((s.nr + chunk - 1) / chunk);
+            for (int ci = 0; ci < nch; ++ci) {
+                const int64_t c0r = (int64_t)ci * chunk, nr = std::min(chunk, s.nr - c0r);
+                JCB_TRY(h2d_2d(c, s.dX + c0r, s.ld, X + s.r0 + c0r, ldx, nr, p, cs));
+                JCB_TRY(h2d_2d(c, s.dY + c0r, s.ld, Y + s.r0 + c0r, ldy, nr, q, cs));
+                JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
+                JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1 + (ci & 1)], 0));
+                if (d == 0 && ci == 0) {
+                    JCB_TRY(launch_pivot(c, s.dX, s.ld, s.dY, s.ld, nr, p, q, s.d_pivot));
+                    JCB_CUDA(cudaEventRecord(c->mg_ev[1], st));      // pivot ready for the peers
+                }
+                JCB_TRY(launch_gram(c, s.dX + c0r, s.ld, s.dY + c0r, s.ld, s.dw ? s.dw + c0r : nullptr, nr, p, q,
+                                    s.d_pivot, s.d_part, ci > 0));
+            }
+        }
+        JCB_CUDA(cudaEventRecord(c->mg_ev[0], st));     // this device's partial Gram is complete
+    }
+    // ---- exchange: every device sums all partial Grams out of peer memory, then solves and scores
+    for (int d = 0; d < nd; ++d) {
+        Ctx* c = dev_ctx(d);
+        Shard& s = sh[d];
+        JCB_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        for (int e = 0; e < nd; ++e)
+            if (e != d) JCB_CUDA(cudaStreamWaitEvent(st, dev_ctx(e)->mg_ev[0], 0));
+        peer_reduce_kernel<<<(int)std::min<int64_t>((plen + 255) / 256, 592), 256, 0, st>>>(s.d_packed, s.d_srcs,
+                                                                                            nd, plen);
+        JCB_LAUNCH_CHECK();
+        JCB_TRY(launch_solve(c, s.d_packed, s.d_pivot, p, q, nlv, scal, s.dP, s.dR, s.dW, s.dC, s.dTT, s.dxm,
+                             s.dxs, s.dym, s.dys, s.d_sumw));
+        if (s.nr > 0) {
+            if (nlv > 0) JCB_TRY(launch_xmul(c, s.dX, s.ld, s.nr, p, s.dxm, s.dxs, s.dR, p, nlv, nullptr, s.dT, s.ld));
+            JCB_TRY(launch_weights(c, s.dw, s.nr, s.d_sumw, s.dwout));
+            if (writeback) {
+                JCB_TRY(launch_center_scale(c, s.dX, s.ld, s.nr, p, s.dxm, s.dxs));
+                JCB_TRY(launch_center_scale(c, s.dY, s.ld, s.nr, q, s.dym, s.dys));
+            }
+            if (nlv > 0) JCB_TRY(d2h_2d(c, T + s.r0, ldt, s.dT, s.ld, s.nr, nlv, st));
+            JCB_TRY(d2h_2d(c, w_out + s.r0, n, s.dwout, s.ld, s.nr, 1, st));
+            if (writeback) {
+                JCB_TRY(d2h_2d(c, X + s.r0, ldx, s.dX, s.ld, s.nr, p, st));
+                JCB_TRY(d2h_2d(c, Y + s.r0, ldy, s.dY, s.ld, s.nr, q, st));
+            }
+        }
+    }
+    {   // model from device 0
+        const Shard& s = sh[0];
+        JCB_CUDA(cudaSetDevice(c0->device));
+        cudaStream_t st = c0->stream;
+        if (nlv > 0) {
+            JCB_CUDA(cudaMemcpyAsync(P, s.dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+            JCB_CUDA(cudaMemcpyAsync(R, s.dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+            JCB_CUDA(cudaMemcpyAsync(W, s.dW, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+            JCB_CUDA(cudaMemcpyAsync(C, s.dC, (size_t)q * nlv * 8, cudaMemcpyDeviceToHost, st));
+            JCB_CUDA(cudaMemcpyAsync(TT, s.dTT, (size_t)nlv * 8, cudaMemcpyDeviceToHost, st));
+        }
+        JCB_CUDA(cudaMemcpyAsync(xmeans, s.dxm, p * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(xscales, s.dxs, p * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(ymeans, s.dym, q * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(yscales, s.dys, q * 8, cudaMemcpyDeviceToHost, st));
+    }
+    // ---- drain every device (a device's partial buffer must outlive its peers' reduce)
+    for (int d = nd - 1; d >= 0; --d) {
+        Ctx* c = dev_ctx(d);
+        JCB_CUDA(cudaSetDevice(c->device));
+        if (d == 0) phase_end(c0, JCB200_T_TOTAL);
+        JCB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    phases_collect(c0);
+    return 0;
+}
+
 }  // namespace jcb
 
 using namespace jcb;
@@ -218,9 +398,58 @@ int jcb200_init(int device) {
     return init_locked(device);
 }
 
+static void destroy_ctx(Ctx* c);
+
+int jcb200_init_multi(int ngpu, const int* device_ids) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    tl_error[0] = 0;
+    if (ngpu < 1 || ngpu > 8 || !device_ids) {
+        set_error("init_multi: ngpu must be 1..8");
+        return JCB200_EINVAL;
+    }
+    if (g_ctx.ready || g_ndev > 1) {
+        set_error("already initialised; call jcb200_shutdown first");
+        return JCB200_EINVAL;
+    }
+    JCB_TRY(init_ctx(&g_ctx, device_ids[0]));
+    for (int d = 1; d < ngpu; ++d) JCB_TRY(init_ctx(&g_extra[d - 1], device_ids[d]));
+    // peer access between every pair (NVLink / NVSwitch): the Gram exchange reads peer memory directly
+    for (int d = 0; d < ngpu; ++d)
+        for (int e = 0; e < ngpu; ++e) {
+            if (d == e) continue;
+            int can = 0;
+            JCB_CUDA(cudaDeviceCanAccessPeer(&can, device_ids[d], device_ids[e]));
+            if (!can) {
+                set_error("devices %d and %d cannot access each other's memory", device_ids[d], device_ids[e]);
+                return JCB200_ENODEV;
+            }
+            JCB_CUDA(cudaSetDevice(device_ids[d]));
+            cudaError_t pe = cudaDeviceEnablePeerAccess(device_ids[e], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+                set_error("cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(pe));
+                return (int)pe;
+            }
+            cudaGetLastError();
+        }
+    g_ndev = ngpu;
+    JCB_CUDA(cudaSetDevice(device_ids[0]));
+    return 0;
+}
+
+int jcb200_device_count(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return g_ctx.ready ? g_ndev : 0;
+}
+
 void jcb200_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
-    Ctx* c = &g_ctx;
+    for (int d = 1; d < g_ndev; ++d) destroy_ctx(&g_extra[d - 1]);
+    g_ndev = 1;
+    destroy_ctx(&g_ctx);
+    pinned_release_all();
+}
+
+static void destroy_ctx(Ctx* c) {
     if (!c->ready) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
@@ -241,7 +470,6 @@ void jcb200_shutdown(void) {
     free_buf(c->cvPk);
     c->cv_hostX = c->cv_hostY = nullptr;
     free_staging(c);
-    pinned_release_all();
     if (c->sched_host) cudaFreeHost(c->sched_host);
     c->sched_host = nullptr;
     c->sched_host_bytes = 0;
@@ -251,6 +479,7 @@ void jcb200_shutdown(void) {
         cudaEventDestroy(c->ev_end[i]);
     }
     for (int i = 0; i < 3; ++i) cudaEventDestroy(c->chunk_ev[i]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(c->mg_ev[i]);
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
         cudaEventDestroy(c->gram_ev0[i]);
         cudaEventDestroy(c->gram_ev1[i]);
@@ -443,6 +672,9 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     if (nlv_out) *nlv_out = nlv;
     ARG_CHECK(nlv == 0 || (T && P && R && W && C && TT && ldt >= n), "plskern_fit: NULL output");
 
+    if (g_ndev > 1 && n >= 65536 * (int64_t)g_ndev)
+        return fit_multi_locked(X, ldx, Y, ldy, w, n, p, q, nlv, scal, writeback_xy, T, ldt, P, R, W, C, TT,
+                                xmeans, xscales, ymeans, yscales, w_out);
     const int64_t ld = even_up(n);
     JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
     JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));

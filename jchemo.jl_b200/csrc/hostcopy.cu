@@ -115,7 +115,7 @@ constexpr size_t SLOT_BYTES = 32u << 20;
 static int ensure_staging(Ctx* c) {
     if (c->stage[0]) return 0;
     for (int s = 0; s < 2; ++s) {
-        JCB_CUDA(cudaHostAlloc(&c->stage[s], SLOT_BYTES, cudaHostAllocDefault));
+        JCB_CUDA(cudaHostAlloc(&c->stage[s], SLOT_BYTES, cudaHostAllocPortable));
         JCB_CUDA(cudaEventCreateWithFlags(&c->stage_ev[s], cudaEventDisableTiming));
     }
     return 0;
@@ -232,7 +232,7 @@ void* pinned_alloc(size_t bytes) {
             return b.p;
         }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }

@@ -62,6 +62,8 @@ struct Ctx {
     int64_t sk_p = -1, sk_q = -1, sk_nst = -1;
     int sk_ngroups = 0, sk_nsegs = 0;
     int64_t sk_zone_len = 0;
+    bool k1_attr_set = false;
+    cudaEvent_t mg_ev[2];           // multi-GPU: [0] pivot / packed ready, [1] reduced
     size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf pivot_ws;

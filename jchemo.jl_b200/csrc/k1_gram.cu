@@ -985,13 +985,12 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     }
 #endif
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->k1_attr_set) {      // function attributes are per device
         JCB_CUDA(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       K1_SMEM));
         JCB_CUDA(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       K1_SMEM));
-        attr_set = true;
+        c->k1_attr_set = true;
     }
     phase_begin(c, JCB200_T_GRAM);
     const int slot = (int)(c->gram_calls % Ctx::GRAM_RING);
