@@ -59,6 +59,17 @@ function check(rc::Cint, what::AbstractString)
     error("JchemoB200.$what failed (status $rc): $msg")
 end
 
+"""
+    init_multi(devices)
+
+Bind the library to several GPUs of one box (e.g. `init_multi(0:7)`); `plskern` / `plskern!` then shard
+the rows over them inside the library (`jcb200_init_multi`).  Call once, before any fit.
+"""
+function init_multi(devices)
+    ids = Cint.(collect(devices))
+    check(ccall((:jcb200_init_multi, LIB), Cint, (Cint, Ptr{Cint}), length(ids), ids), "init_multi")
+end
+
 # ---------------------------------------------------------------- fit (src/plskern.jl:106-178)
 function _fit(X::Matrix{Float64}, Y::Matrix{Float64}, weights, nlv::Integer, scal::Bool, writeback::Bool)
     n, p = size(X)
