@@ -315,3 +315,20 @@ def test_empty_new_data(jc):
         jc.predict(fm, np.zeros((3, 5)))
     with pytest.raises(jc.JchemoB200Error):
         jc.plskern(np.empty((0, 6), order="F"), np.empty((0, 2), order="F"), nlv=1)     # n = 0 is rejected
+
+
+def test_single_process_multi_gpu():
+    """jcb200_init_multi: the host-pointer fit sharded over 2 GPUs inside the library (peer-memory Gram
+    reduce) against the oracle.  Needs a fresh process (the library binds its devices once) and 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JCB_SKIP_E2E="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "bench", "multigpu_inproc.py"), "2"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert '"parity_ok": true' in res.stdout
