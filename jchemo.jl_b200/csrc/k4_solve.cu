@@ -455,7 +455,13 @@ lvloop_kernel(const LvParams prm) {
                 s += t * t;
             }
             const double nrm = sqrt(block_sum(s, red));
-            for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+            if (nrm > 0.0) {
+                for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+            } else {
+                // XtY == 0 (e.g. constant Y): LAPACK's svd of a zero matrix returns U = I, so the
+                // reference takes w = e_1 (plskern.jl:154) and carries on with c = 0
+                for (int k = tid; k < p; k += LV_THREADS) w_s[k] = (k == 0) ? 1.0 : 0.0;
+            }
         }
         __syncthreads();
         LV_MARK(3);
@@ -537,7 +543,9 @@ lvloop_kernel(const LvParams prm) {
         }
         const double tt = block_sum(s, red);
         __syncthreads();
-        for (int j = tid; j < q; j += LV_THREADS) c_s[j] /= tt;
+        // tt == 0 (r = 0: XtY vanished, more LVs asked than the data carry): the reference divides 0/0;
+        // here the LV is inert (c = 0, P = 0) so predictions stay finite
+        for (int j = tid; j < q; j += LV_THREADS) c_s[j] = tt > 0.0 ? c_s[j] / tt : 0.0;
         __syncthreads();
         LV_MARK(7);
         // ---------------------------------------------------------------- (5) deflate, store
@@ -556,7 +564,7 @@ lvloop_kernel(const LvParams prm) {
             }
         }
         for (int i = lo + tid; i < hi; i += LV_THREADS) {
-            __stcg(prm.P + i + (int64_t)a * P64, zp_s[i] / tt);
+            __stcg(prm.P + i + (int64_t)a * P64, tt > 0.0 ? zp_s[i] / tt : 0.0);
             __stcg(prm.R + i + (int64_t)a * P64, r_s[i]);
             prm.W[i + (int64_t)a * P64] = w_s[i];
         }
@@ -569,7 +577,7 @@ lvloop_kernel(const LvParams prm) {
             double* Pw = prm.Ppriv + (int64_t)rank * P64 * nlv + (int64_t)a * P64;
             double* Rw = prm.Rpriv + (int64_t)rank * P64 * nlv + (int64_t)a * P64;
             for (int i = tid; i < p; i += LV_THREADS) {
-                __stcg(Pw + i, zp_s[i] / tt);
+                __stcg(Pw + i, tt > 0.0 ? zp_s[i] / tt : 0.0);
                 __stcg(Rw + i, r_s[i]);
             }
             __syncthreads();

@@ -332,3 +332,21 @@ def test_single_process_multi_gpu():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert '"parity_ok": true' in res.stdout
+
+
+def test_constant_y_multiresponse(jc):
+    """Constant Y with q > 1.  After centring XtY is rounding noise (or exactly zero): predictions must
+    stay at ymeans.  For XtY == 0 exactly the reference's svd(XtY).U[:, 1] is e_1 (LAPACK returns U = I for
+    a zero matrix, plskern.jl:154) and c = 0; the device path must do the same instead of 0/0."""
+    X = synth.synth_matrix(1, 200, 12)
+    Y = np.tile(np.array([[3.0, -1.5]]), (200, 1))
+    fm = jc.plskern(X, Y, nlv=2)
+    ref = oracle.plskern(X, Y, nlv=2)
+    np.testing.assert_allclose(jc.predict(fm, X[:5]).pred, oracle.predict(ref, X[:5]), atol=1e-12)
+    Y0 = np.zeros((200, 2))                       # exactly zero after centring: XtY == 0 exactly
+    fm0 = jc.plskern(X, Y0, nlv=1)
+    ref0 = oracle.plskern(X, Y0, nlv=1)
+    assert np.all(np.isfinite(fm0.T)) and np.all(fm0.C == 0) and np.all(ref0.C == 0)
+    assert abs(abs(fm0.W[0, 0]) - 1.0) < 1e-15 and np.all(fm0.W[1:, 0] == 0)        # w = e_1
+    assert relerr(fm0.T * np.sign(fm0.W[0, 0] * ref0.W[0, 0]), ref0.T) < TOL
+    np.testing.assert_allclose(jc.predict(fm0, X[:5]).pred, 0.0, atol=1e-300)
