@@ -152,6 +152,18 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
                   int32_t k_hi, int32_t scal, int32_t reuse_xy, double* ssr, double* sumres, double* ysum,
                   double* ysumsq);
 
+/* locwlv for fun = plskern (next row) — /root/reference/src/locwlv.jl:9-48: for every row i
+ * of X (m x p) a weighted kernel-PLS fit on its neighbours Xtrain[s_i, :], Ytrain[s_i, :] (s_i =
+ * nn_idx[nn_off[i] : nn_off[i+1]], zero based; weights nn_w likewise or NULL for ones) with
+ * min(k_i, p, k_hi) LVs, then the prediction of row i for every nlv in k_lo..k_hi (a model with fewer LVs
+ * answers with all it has; the reference throws there — locwlv.jl:37 — and the host mirrors raise before calling).  pred is m x q x nk column-major
+ * (the reference's zpred).  One CTA per row runs the whole tiny fit: thousands of fits in one launch.
+ * q == 1 with identical neighbour responses returns that value (locwlv.jl:24-28).  q <= 16. */
+int jcb200_locw_plskern(const double* Xtrain, int64_t ldxt, const double* Ytrain, int64_t ldyt, int64_t ntr,
+                        int64_t p, int64_t q, const double* X, int64_t ldx, int64_t m, const int64_t* nn_idx,
+                        const int64_t* nn_off, const double* nn_w, int32_t k_lo, int32_t k_hi, int32_t scal,
+                        double* pred);
+
 /* Base.summary(::Plsr, X) (next row) — /root/reference/src/plskern.jl:246-260: explained
  * X-variance per LV.  One pass over X for sstot = sum(weights' * ((X - xmeans)./xscales).^2); then
  * tt_adj = colsum(P.^2) .* TT, pvar = tt_adj / sstot, cumpvar = cumsum(pvar), xvar = tt_adj / n

@@ -8,9 +8,9 @@ from ._lib import JchemoB200Error, lib, last_timings, LIB_PATH, SIGNATURES  # no
 from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict, summary,  # noqa: F401
                       ensure_mat, CoefResult, PredResult)
 
-from .gridscore import gridscorelv, gridcvlv, residual_sums  # noqa: F401
+from .gridscore import gridscorelv, gridcvlv, locwlv, residual_sums  # noqa: F401
 
-__all__ = ["gridscorelv", "gridcvlv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "ensure_mat",
+__all__ = ["gridscorelv", "gridcvlv", "locwlv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "ensure_mat",
            "JchemoB200Error", "lib", "last_timings"]
 
 

@@ -456,6 +456,7 @@ static void destroy_ctx(Ctx* c) {
     free_buf(c->partials);
     free_buf(c->sched_dev);
     free_buf(c->pivot_ws);
+    free_buf(c->locw_ws);
     free_buf(c->solve_ws);
     free_buf(c->xmul_ws);
     free_buf(c->hX);
@@ -1144,6 +1145,64 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
                               ssr + (size_t)j * nk * q, sumres + (size_t)j * nk * q, ysum + (size_t)j * q,
                               ysumsq + (size_t)j * q);
     }
+    return 0;
+}
+
+int jcb200_locw_plskern(const double* Xtrain, int64_t ldxt, const double* Ytrain, int64_t ldyt, int64_t ntr,
+                        int64_t p, int64_t q, const double* X, int64_t ldx, int64_t m, const int64_t* nn_idx,
+                        const int64_t* nn_off, const double* nn_w, int32_t k_lo, int32_t k_hi, int32_t scal,
+                        double* pred) {
+    API_PROLOGUE();
+    ARG_CHECK(Xtrain && Ytrain && X && nn_idx && nn_off && pred && ntr > 0 && p > 0 && q > 0 && m > 0 &&
+                  ldxt >= ntr && ldyt >= ntr && ldx >= m && k_lo >= 0 && k_hi >= k_lo,
+              "locw_plskern: bad argument");
+    ARG_CHECK(nn_off[0] == 0, "locw_plskern: nn_off[0] must be 0");
+    int64_t kmax = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        const int64_t k = nn_off[i + 1] - nn_off[i];
+        ARG_CHECK(k >= 1, "locw_plskern: every row needs at least one neighbour");
+        kmax = std::max(kmax, k);
+    }
+    const int64_t ntot = nn_off[m];
+    for (int64_t e = 0; e < ntot; ++e)
+        ARG_CHECK(nn_idx[e] >= 0 && nn_idx[e] < ntr, "locw_plskern: neighbour index out of range");
+    const int nk = k_hi - k_lo + 1;
+    const int64_t ldt = even_up(ntr), ldq = even_up(m);
+    JCB_TRY(ensure(c->hX, (size_t)ldt * p * 8));
+    JCB_TRY(ensure(c->hY, (size_t)ldt * q * 8));
+    JCB_TRY(ensure(c->hT, (size_t)ldq * p * 8));
+    JCB_TRY(ensure(c->hPred, (size_t)m * q * nk * 8));
+    JCB_TRY(ensure(c->cvIdx, (size_t)(ntot + m + 1) * 8));
+    JCB_TRY(ensure(c->hW, (size_t)std::max<int64_t>(ntot, 2) * 8));
+    c->cv_hostX = c->cv_hostY = nullptr;       // hX / hY no longer hold a gridcv copy
+    double* dXt = (double*)c->hX.p;
+    double* dYt = (double*)c->hY.p;
+    double* dXq = (double*)c->hT.p;
+    double* dPred = (double*)c->hPred.p;
+    int64_t* dIdx = (int64_t*)c->cvIdx.p;
+    int64_t* dOff = dIdx + ntot;
+    double* dWn = nn_w ? (double*)c->hW.p : nullptr;
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_TRY(h2d_2d(c, dXt, ldt, Xtrain, ldxt, ntr, p, st));
+    JCB_TRY(h2d_2d(c, dYt, ldt, Ytrain, ldyt, ntr, q, st));
+    JCB_TRY(h2d_2d(c, dXq, ldq, X, ldx, m, p, st));
+    JCB_CUDA(cudaMemcpyAsync(dIdx, nn_idx, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dOff, nn_off, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nn_w) JCB_CUDA(cudaMemcpyAsync(dWn, nn_w, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+    phase_end(c, JCB200_T_H2D);
+    phase_begin(c, JCB200_T_SCORES);
+    JCB_TRY(launch_locw(c, dXt, ldt, dYt, ldt, ntr, dXq, ldq, m, p, q, dIdx, dOff, dWn, (int)kmax, k_lo, k_hi,
+                        scal, dPred));
+    phase_end(c, JCB200_T_SCORES);
+    phase_begin(c, JCB200_T_D2H);
+    JCB_CUDA(cudaMemcpyAsync(pred, dPred, (size_t)m * q * nk * 8, cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_D2H);
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
     return 0;
 }
 

@@ -67,6 +67,7 @@ struct Ctx {
     size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf pivot_ws;
+    Buf locw_ws;
     Buf solve_ws;
     Buf xmul_ws;
     // general scratch for the host-pointer API
@@ -128,6 +129,9 @@ int launch_fill_uniform(Ctx* c, double* d, int64_t ld, int64_t n_rows, int64_t n
                         uint64_t seed, int64_t row0, int64_t n_global);
 int launch_sstot(Ctx* c, const double* dX, int64_t ldx, int64_t n, int64_t p, const double* dmu,
                  const double* dsigma, const double* dw, double* dpartial, int gx, double* dout);
+int launch_locw(Ctx* c, const double* dXtr, int64_t ldxt, const double* dYtr, int64_t ldyt, int64_t ntr,
+                const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q, const int64_t* d_idx,
+                const int64_t* d_off, const double* d_w, int kmax, int k_lo, int k_hi, int scal, double* d_pred);
 int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmeans,
                 const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
                 int64_t q, int k, double* dB, double* dint);

@@ -140,3 +140,42 @@ def gridcvlv(X, Y, *, segm, score, nlv, fun=plskern, scal=False):
         pass
     from collections import namedtuple
     return namedtuple("GridcvResult", ["res", "res_rep"])(res, res_rep)
+
+
+def locwlv(Xtrain, Ytrain, X, *, listnn, listw=None, fun=plskern, nlv, scal=False):
+    """locwlv(Xtrain, Ytrain, X; listnn, listw = nothing, fun = plskern, nlv) -> (pred = ...,), reference
+    `/root/reference/src/locwlv.jl:9-48`: one weighted kernel-PLS fit per row of X on its neighbours
+    `listnn[i]` (zero-based row indices of Xtrain) with weights `listw[i]`, predictions for every nlv of the
+    clamped range.  All m tiny fits run in ONE kernel launch (`jcb200_locw_plskern`, next row SURVEY 8f-4)."""
+    from .plskern import PredResult
+    if fun is not plskern:
+        raise TypeError("the batched path covers fun = plskern")
+    Xtrain, Ytrain, X = _fmat(Xtrain), _fmat(Ytrain), _fmat(X)
+    ntr, p = Xtrain.shape
+    q = Ytrain.shape[1]
+    m = X.shape[0]
+    if X.shape[1] != p or Ytrain.shape[0] != ntr or len(listnn) != m:
+        raise ValueError("DimensionMismatch in locwlv")
+    ks = np.atleast_1d(np.asarray(nlv))
+    lo, hi = max(0, int(ks.min())), min(p, int(ks.max()))                        # locwlv.jl:14
+    nk = hi - lo + 1
+    segs = [np.atleast_1d(np.asarray(s, dtype=np.int64)) for s in listnn]
+    off = np.ascontiguousarray(np.concatenate([[0], np.cumsum([s.size for s in segs])]).astype(np.int64))
+    idx = np.ascontiguousarray(np.concatenate(segs))
+    for i, sg in enumerate(segs):
+        # predict(fm; nlv = k) with k above the model's LV count gives an empty range and the reference's
+        # zpred assignment throws (locwlv.jl:37, plskern.jl:229); the C entry point would clamp instead
+        if min(sg.size, p) < hi and not (q == 1 and np.unique(Ytrain[sg]).size == 1):
+            raise ValueError(f"DimensionMismatch: neighbourhood {i} has {sg.size} rows, fewer than nlv = {hi}")
+    w = None
+    if listw is not None:
+        w = np.ascontiguousarray(np.concatenate([np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in listw]))
+        if w.size != idx.size:
+            raise ValueError("listw does not match listnn")
+    pred = np.empty((m, q, nk), order="F")
+    rc = _lib.lib().jcb200_locw_plskern(_ptr(Xtrain), _ld(Xtrain), _ptr(Ytrain), _ld(Ytrain), ntr, p, q, _ptr(X),
+                                        _ld(X), m, _ptr(idx), _ptr(off), _ptr(w), lo, hi, 1 if scal else 0,
+                                        _ptr(pred))
+    _lib.check(rc, "locwlv")
+    out = [np.asfortranarray(pred[:, :, a]) for a in range(nk)]
+    return PredResult(out[0] if nk == 1 else out)

@@ -17,7 +17,7 @@ module JchemoB200
 using LinearAlgebra
 using Libdl
 
-export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv
+export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv, locwlv
 
 const LIB = get(ENV, "JCHEMO_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
@@ -280,6 +280,36 @@ function gridcvlv(X, Y; segm, score::Symbol, nlv, scal = false)
     uk = sort(unique(ks))
     res = (; nlv = uk, (Symbol("y", c) => [sum(ys[c][ks .== k]) / count(ks .== k) for k in uk] for c in 1:q)...)
     (res = res, res_rep = res_rep)
+end
+
+# ---------------------------------------------------------------- locwlv (src/locwlv.jl:9-48)
+"""
+    locwlv(Xtrain, Ytrain, X; listnn, listw = nothing, nlv, scal = false)
+
+`Jchemo.locwlv` for `fun = plskern`: every row of `X` is predicted by a weighted kernel-PLS model fitted on
+its neighbours; all `m` tiny fits run in one kernel launch (`jcb200_locw_plskern`).
+"""
+function locwlv(Xtrain, Ytrain, X; listnn, listw = nothing, nlv, scal = false, verbose = false)
+    Xtrain = dense64(ensure_mat(Xtrain)); Ytrain = dense64(ensure_mat(Ytrain)); X = dense64(ensure_mat(X))
+    ntr, p = size(Xtrain); q = nco(Ytrain); m = nro(X)
+    lo = max(0, minimum(nlv)); hi = min(p, maximum(nlv)); nk = hi - lo + 1        # :14
+    for i in 1:m
+        k = length(listnn[i])
+        if min(k, p) < hi && !(q == 1 && length(unique(Ytrain[listnn[i], :])) == 1)
+            throw(DimensionMismatch("neighbourhood $i has $k rows, fewer than nlv = $hi"))   # as :37
+        end
+    end
+    idx = Int64.(reduce(vcat, [collect(s) for s in listnn])) .- 1
+    off = Int64.(vcat(0, cumsum([length(s) for s in listnn])))
+    w = isnothing(listw) ? C_NULL : Float64.(reduce(vcat, [collect(v) for v in listw]))
+    zpred = Array{Float64}(undef, m, q, nk)
+    rc = ccall((:jcb200_locw_plskern, LIB), Cint,
+               (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64,
+                Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Int32, Int32, Ptr{Float64}),
+               Xtrain, ntr, Ytrain, ntr, ntr, p, q, X, m, m, idx, off, w, lo, hi, scal, zpred)
+    check(rc, "locwlv")
+    pred = [zpred[:, :, a] for a in 1:nk]
+    (pred = nk == 1 ? pred[1] : pred,)
 end
 
 end # module

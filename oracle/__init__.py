@@ -19,4 +19,4 @@ from .plskern_ref import (  # noqa: F401
     Plsr, plskern, plskern_bang, transform, coef, predict, summary, sign_align,
 )
 from .nipals_ref import plsnipals  # noqa: F401
-from .gridscore_ref import gridscorelv, gridcvlv  # noqa: F401
+from .gridscore_ref import gridscorelv, gridcvlv, locwlv  # noqa: F401

@@ -95,3 +95,26 @@ def gridcvlv(X, Y, *, segm, score, nlv, fun=plskern, **kwargs):
     for c in range(q):
         res[f"y{c + 1}"] = np.array([arr[res_rep["nlv"] == k, 3 + c].mean() for k in ks])
     return res, res_rep
+
+
+def locwlv(Xtrain, Ytrain, X, *, listnn, listw=None, nlv, fun=plskern, **kwargs):
+    """locwlv.jl:9-48 — one fit per row of X on its neighbours, predictions for the clamped nlv range;
+    zero-based neighbour indices.  Returns a list of m x q matrices (a single matrix for one nlv)."""
+    Xtrain, Ytrain, X = ensure_mat(Xtrain), ensure_mat(Ytrain), ensure_mat(X)
+    p, m, q = Xtrain.shape[1], X.shape[0], Ytrain.shape[1]
+    ks = np.atleast_1d(np.asarray(nlv))
+    lo, hi = max(0, int(ks.min())), min(p, int(ks.max()))                 # :14
+    nk = hi - lo + 1
+    zpred = np.empty((m, q, nk))
+    for i in range(m):                                                    # :18
+        s = np.atleast_1d(np.asarray(listnn[i]))
+        zY = Ytrain[s]
+        if q == 1 and np.unique(zY).size == 1:                            # :24-28
+            zpred[i, :, :] = zY[0, 0]
+            continue
+        wi = None if listw is None else listw[i]
+        fm = fun(Xtrain[s], zY, wi, nlv=hi, **kwargs)                     # :30-34
+        for a in range(nk):
+            zpred[i, :, a] = predict(fm, X[i:i + 1], nlv=lo + a)          # :36-38
+    out = [zpred[:, :, a] for a in range(nk)]
+    return out[0] if nk == 1 else out

@@ -350,3 +350,36 @@ def test_constant_y_multiresponse(jc):
     assert abs(abs(fm0.W[0, 0]) - 1.0) < 1e-15 and np.all(fm0.W[1:, 0] == 0)        # w = e_1
     assert relerr(fm0.T * np.sign(fm0.W[0, 0] * ref0.W[0, 0]), ref0.T) < TOL
     np.testing.assert_allclose(jc.predict(fm0, X[:5]).pred, 0.0, atol=1e-300)
+
+
+@pytest.mark.parametrize("q,scal,weighted", [(1, False, True), (3, True, True), (2, False, False)])
+def test_locwlv_batched_tiny_fits(jc, q, scal, weighted):
+    """Next row: locwlv for fun = plskern — one tiny weighted fit per query row, all in one
+    kernel launch — against the oracle's loop of fits (locwlv.jl:9-48).  Ragged neighbourhoods, one (q = 1)
+    whose neighbours share a single Y value; a neighbourhood smaller than nlv throws as the reference does."""
+    rng = np.random.default_rng(7)
+    ntr, p, m, nlv = 400, 37, 23, 6
+    Xtr = synth.synth_matrix(1, ntr, p)
+    Ytr = synth.synth_matrix(2, ntr, q) + Xtr[:, :q] * 2.0
+    X = synth.synth_matrix(4, m, p)
+    listnn, listw = [], []
+    for i in range(m):
+        k = [9, 60, 33, 100][i % 4]
+        s = np.sort(rng.choice(ntr, size=k, replace=False))
+        listnn.append(s)
+        listw.append(0.2 + rng.random(k))
+    if q == 1:
+        Ytr[listnn[5], 0] = 1.25                      # all neighbours of row 5 share one value
+    got = jc.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw if weighted else None, nlv=range(0, nlv + 1),
+                    scal=scal).pred
+    ref = oracle.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw if weighted else None, nlv=range(0, nlv + 1),
+                        scal=scal)
+    assert len(got) == len(ref) == nlv + 1
+    for a in range(nlv + 1):
+        assert relerr(got[a], ref[a]) < 1e-9, a       # k = 9 neighbourhoods are fitted close to full rank
+    listnn[2] = listnn[2][:4]
+    listw[2] = listw[2][:4]
+    with pytest.raises(ValueError):
+        jc.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw, nlv=nlv)
+    with pytest.raises(ValueError):
+        oracle.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw, nlv=nlv)
