@@ -152,6 +152,13 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
                   int32_t k_hi, int32_t scal, int32_t reuse_xy, double* ssr, double* sumres, double* ysum,
                   double* ysumsq);
 
+/* xfit / xresid (next row) — /root/reference/src/xfit.jl:33-56 and :88-99.
+ * resid == 0: out = ((X - xmeans)/xscales) R[:, 1:nlv] P[:, 1:nlv]' * diag(xscales) + xmeans  (X_fit, original
+ * scale; nlv == 0 gives every row = xmeans, xfit.jl:41-45).  resid != 0: out = X - X_fit.
+ * X m x p (ldx), out m x p (ldo); out may alias X (the bang forms overwrite their argument). */
+int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double* xmeans, const double* xscales,
+                const double* R, const double* P, int32_t nlv, int32_t resid, double* out, int64_t ldo);
+
 /* locwlv for fun = plskern (next row) — /root/reference/src/locwlv.jl:9-48: for every row i
  * of X (m x p) a weighted kernel-PLS fit on its neighbours Xtrain[s_i, :], Ytrain[s_i, :] (s_i =
  * nn_idx[nn_off[i] : nn_off[i+1]], zero based; weights nn_w likewise or NULL for ones) with

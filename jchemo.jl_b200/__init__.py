@@ -6,11 +6,12 @@ include/jchemo_b200.h); this package is the host-side mirror of the reference's 
 """
 from ._lib import JchemoB200Error, lib, last_timings, LIB_PATH, SIGNATURES  # noqa: F401
 from .plskern import (Plsr, plskern, plskern_bang, transform, coef, predict, summary,  # noqa: F401
-                      ensure_mat, CoefResult, PredResult)
+                      xfit, xfit_bang, xresid, xresid_bang, ensure_mat, CoefResult, PredResult)
 
 from .gridscore import gridscorelv, gridcvlv, locwlv, residual_sums  # noqa: F401
 
-__all__ = ["gridscorelv", "gridcvlv", "locwlv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "ensure_mat",
+__all__ = ["gridscorelv", "gridcvlv", "locwlv", "Plsr", "plskern", "plskern_bang", "transform", "coef", "predict", "summary", "xfit", "xfit_bang",
+           "xresid", "xresid_bang", "ensure_mat",
            "JchemoB200Error", "lib", "last_timings"]
 
 

@@ -41,6 +41,8 @@ SIGNATURES = {
                                    i32] + [C.c_void_p] * 4 + [i32, i32] + [C.c_void_p] * 4),
     "jcb200_gridcv": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.c_void_p, i32,
                                 i32, i32, i32, i32] + [C.c_void_p] * 4),
+    "jcb200_xfit": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32,
+                              C.c_void_p, i64]),
     "jcb200_locw_plskern": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p, i64, i64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, C.c_void_p]),
     "jcb200_summary": (C.c_int, [C.c_void_p, i64, i64, i64] + [C.c_void_p] * 5 + [i32] + [C.c_void_p] * 3),

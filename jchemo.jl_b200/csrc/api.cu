@@ -806,6 +806,49 @@ int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const d
     return 0;
 }
 
+int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double* xmeans, const double* xscales,
+                const double* R, const double* P, int32_t nlv, int32_t resid, double* out, int64_t ldo) {
+    API_PROLOGUE();
+    ARG_CHECK(X && xmeans && xscales && out && m > 0 && p > 0 && nlv >= 0 && ldx >= m && ldo >= m,
+              "xfit: bad argument");
+    ARG_CHECK(nlv == 0 || (R && P), "xfit: NULL R or P");
+    const int64_t ld = even_up(m);
+    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    JCB_TRY(ensure(c->hT, (size_t)ld * std::max<int>(nlv, 1) * 8));
+    JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + 2 * (size_t)p * nlv + 16) * 8));
+    c->cv_hostX = c->cv_hostY = nullptr;
+    double* dX = (double*)c->hX.p;
+    double* dT = (double*)c->hT.p;
+    Carver cv(c->hSmall.p);
+    double* dxm = cv.take(p);
+    double* dxs = cv.take(p);
+    double* dR = cv.take((size_t)p * nlv);
+    double* dP = cv.take((size_t)p * nlv);
+    cudaStream_t st = c->stream;
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    phase_begin(c, JCB200_T_H2D);
+    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
+    JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
+    JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
+    if (nlv > 0) {
+        JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
+        JCB_CUDA(cudaMemcpyAsync(dP, P, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
+    }
+    phase_end(c, JCB200_T_H2D);
+    phase_begin(c, JCB200_T_SCORES);
+    if (nlv > 0) JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
+    JCB_TRY(launch_xfit(c, dX, ld, m, p, dT, ld, dP, p, nlv, dxm, dxs, resid));
+    phase_end(c, JCB200_T_SCORES);
+    phase_begin(c, JCB200_T_D2H);
+    JCB_TRY(d2h_2d(c, out, ldo, dX, ld, m, p, st));
+    phase_end(c, JCB200_T_D2H);
+    phase_end(c, JCB200_T_TOTAL);
+    JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
+    return 0;
+}
+
 int jcb200_coef(const double* R, const double* C, const double* xmeans, const double* xscales,
                 const double* ymeans, const double* yscales, int64_t p, int64_t q, int32_t k,
                 double* B, double* intercept) {

@@ -1,0 +1,87 @@
+// K10 — xfit / xresid (next row): X_fit = (T P') * diag(xscales) + 1 xmeans' and E = X - X_fit,
+// /root/reference/src/xfit.jl:33-56 and :88-99.  T = ((X - xmeans) / xscales) R comes from K5; this kernel is
+// the second skinny product, fused with the return to the original scale (scale! by 1 ./ xscales then
+// center! by -xmeans, xfit.jl:50-53) and, for xresid, with the subtraction from X.  The result overwrites the
+// X slab in HBM (as xfit! overwrites its argument), so the m x p output needs no second buffer.
+//
+// HBM-bound on the m x p write (plus the read of X for xresid): 8 m p (16 m p) bytes against 2 m p nlv flops.
+#include "jcb_internal.cuh"
+
+namespace jcb {
+
+constexpr int XF_MT = 128;    // rows per CTA tile
+constexpr int XF_NT = 64;     // columns per CTA tile
+constexpr int XF_KC = 32;     // LVs per staged chunk
+
+// thread (tx = tid & 15, ty = tid >> 4): rows 8 tx .. 8 tx + 7, columns 4 ty .. 4 ty + 3 of the tile
+__global__ void __launch_bounds__(256) xfit_kernel(double* __restrict__ X, int64_t ldx, int64_t m, int p,
+                                                   const double* __restrict__ T, int64_t ldt,
+                                                   const double* __restrict__ P, int64_t ldp, int nlv,
+                                                   const double* __restrict__ xm, const double* __restrict__ xs,
+                                                   int resid) {
+    __shared__ __align__(16) double Ts[XF_KC][XF_MT];
+    __shared__ __align__(16) double Ps[XF_KC][XF_NT];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t r0 = (int64_t)blockIdx.x * XF_MT;
+    const int c0 = blockIdx.y * XF_NT;
+    double acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.0;
+    for (int k0 = 0; k0 < nlv; k0 += XF_KC) {
+        const int kc = min(XF_KC, nlv - k0);
+        __syncthreads();
+        for (int e = tid; e < kc * XF_MT; e += 256) {
+            const int k = e / XF_MT, r = e - k * XF_MT;
+            Ts[k][r] = (r0 + r < m) ? T[r0 + r + (int64_t)(k0 + k) * ldt] : 0.0;
+        }
+        for (int e = tid; e < kc * XF_NT; e += 256) {
+            const int k = e / XF_NT, j = e - k * XF_NT;
+            Ps[k][j] = (c0 + j < p) ? P[c0 + j + (int64_t)(k0 + k) * ldp] : 0.0;
+        }
+        __syncthreads();
+        for (int k = 0; k < kc; ++k) {
+            double tv[8], pv[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&Ts[k][8 * tx + i]);
+                tv[i] = v.x;
+                tv[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&Ps[k][4 * ty + j]);
+                pv[j] = v.x;
+                pv[j + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][i] = fma(tv[i], pv[j], acc[j][i]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int col = c0 + 4 * ty + j;
+        if (col >= p) continue;
+        const double mu = xm[col], sc = xs[col];
+        double* dst = X + (int64_t)col * ldx + r0 + 8 * tx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + 8 * tx + i >= m) break;
+            const double fit = acc[j][i] * sc + mu;      // scale!(X, 1 ./ xscales); center!(X, -xmeans)
+            dst[i] = resid ? dst[i] - fit : fit;         // xresid: X .- xfit(...)
+        }
+    }
+}
+
+int launch_xfit(Ctx* c, double* dX, int64_t ldx, int64_t m, int64_t p, const double* dT, int64_t ldt,
+                const double* dP, int64_t ldp, int nlv, const double* dxm, const double* dxs, int resid) {
+    dim3 grid((unsigned)((m + XF_MT - 1) / XF_MT), (unsigned)((p + XF_NT - 1) / XF_NT));
+    xfit_kernel<<<grid, 256, 0, c->stream>>>(dX, ldx, m, (int)p, dT, ldt, dP, ldp, nlv, dxm, dxs, resid);
+    JCB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace jcb

@@ -17,7 +17,7 @@ module JchemoB200
 using LinearAlgebra
 using Libdl
 
-export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv, locwlv
+export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv, locwlv, xfit, xfit!, xresid, xresid!
 
 const LIB = get(ENV, "JCHEMO_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
@@ -281,6 +281,26 @@ function gridcvlv(X, Y; segm, score::Symbol, nlv, scal = false)
     res = (; nlv = uk, (Symbol("y", c) => [sum(ys[c][ks .== k]) / count(ks .== k) for k in uk] for c in 1:q)...)
     (res = res, res_rep = res_rep)
 end
+
+# ---------------------------------------------------------------- xfit / xresid (src/xfit.jl:33-99)
+function _xfit!(object::Plsr, X::Matrix{Float64}, out::Matrix{Float64}, nlv, resid::Bool)
+    a = size(object.T, 2)
+    nlv = isnothing(nlv) ? a : max(min(nlv, a), 0)
+    m, p = size(X)
+    p == size(object.R, 1) || throw(DimensionMismatch("X has $p columns, the model has $(size(object.R, 1))"))
+    m == 0 && return out
+    rc = ccall((:jcb200_xfit, LIB), Cint,
+               (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Int32, Int32, Ptr{Float64}, Int64),
+               X, m, m, p, object.xmeans, object.xscales, nlv == 0 ? C_NULL : object.R,
+               nlv == 0 ? C_NULL : object.P, nlv, resid, out, m)
+    check(rc, "xfit")
+    out
+end
+xfit(object::Plsr, X; nlv = nothing) = (Z = dense64(ensure_mat(X)); _xfit!(object, Z, similar(Z), nlv, false))
+xfit!(object::Plsr, X::Matrix{Float64}; nlv = nothing) = _xfit!(object, X, X, nlv, false)
+xresid(object::Plsr, X; nlv = nothing) = (Z = dense64(ensure_mat(X)); _xfit!(object, Z, similar(Z), nlv, true))
+xresid!(object::Plsr, X::Matrix{Float64}; nlv = nothing) = _xfit!(object, X, X, nlv, true)
 
 # ---------------------------------------------------------------- locwlv (src/locwlv.jl:9-48)
 """

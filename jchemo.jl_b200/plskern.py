@@ -155,6 +155,53 @@ def transform(obj, X, *, nlv=None):
     return T
 
 
+def _xfit(obj, X, nlv, resid, out):
+    a = obj.T.shape[1]
+    nlv = a if nlv is None else min(int(nlv), a)
+    nlv = max(nlv, 0)
+    m, p = X.shape
+    if p != obj.R.shape[0]:
+        raise ValueError(f"DimensionMismatch: X has {p} columns, the model has {obj.R.shape[0]}")
+    if m > 0:
+        R, P = np.asfortranarray(obj.R), np.asfortranarray(obj.P)
+        rc = _lib.lib().jcb200_xfit(_ptr(X), _ld(X), m, p, _ptr(obj.xmeans), _ptr(obj.xscales),
+                                    _ptr(R) if nlv else None, _ptr(P) if nlv else None, nlv, resid, _ptr(out),
+                                    _ld(out))
+        _lib.check(rc, "xfit")
+    return out
+
+
+def _bang_mat(X, name):
+    if not (isinstance(X, np.ndarray) and X.ndim == 2 and X.dtype == np.float64 and X.flags.f_contiguous
+            and X.flags.writeable):
+        raise TypeError(f"MethodError: {name} needs a writeable column-major float64 matrix (X::Matrix)")
+    return X
+
+
+def xfit(obj, X, *, nlv=None):
+    """xfit(object::Plsr, X; nlv = nothing), `/root/reference/src/xfit.jl:33-35`: X_fit in the original scale."""
+    X = _fmat(X)
+    return _xfit(obj, X, nlv, 0, np.empty(X.shape, order="F"))
+
+
+def xfit_bang(obj, X, *, nlv=None):
+    """xfit!(object, X::Matrix; nlv) (xfit.jl:37-56): X is overwritten by X_fit."""
+    X = _bang_mat(X, "xfit!")
+    return _xfit(obj, X, nlv, 0, X)
+
+
+def xresid(obj, X, *, nlv=None):
+    """xresid(object, X; nlv = nothing) (xfit.jl:88-90): E = X - X_fit."""
+    X = _fmat(X)
+    return _xfit(obj, X, nlv, 1, np.empty(X.shape, order="F"))
+
+
+def xresid_bang(obj, X, *, nlv=None):
+    """xresid!(object, X::Matrix; nlv) (xfit.jl:92-99): X is overwritten by the residuals."""
+    X = _bang_mat(X, "xresid!")
+    return _xfit(obj, X, nlv, 1, X)
+
+
 def coef(obj, *, nlv=None):
     """coef(object; nlv = nothing) -> (B = B, int = int) (:207-217)."""
     a = obj.T.shape[1]

@@ -16,7 +16,7 @@ must give the same model, (2) the algebraic invariants of a PLS fit, and
 """
 from .synth import synth_matrix, synth_weights, u01  # noqa: F401
 from .plskern_ref import (  # noqa: F401
-    Plsr, plskern, plskern_bang, transform, coef, predict, summary, sign_align,
+    Plsr, plskern, plskern_bang, transform, coef, predict, summary, xfit, xresid, sign_align,
 )
 from .nipals_ref import plsnipals  # noqa: F401
 from .gridscore_ref import gridscorelv, gridcvlv, locwlv  # noqa: F401

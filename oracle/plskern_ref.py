@@ -205,6 +205,26 @@ def summary(obj, X):
     return {"nlv": np.arange(1, nlv + 1), "var": tt_adj / n, "pvar": pvar, "cumpvar": np.cumsum(pvar)}
 
 
+def xfit(obj, X, *, nlv=None):
+    """xfit.jl:33-56 — X_fit = transform(X) P' in the original scale; nlv = 0 gives rows of xmeans."""
+    X = np.array(ensure_mat(X), dtype=np.float64, order="F", copy=True)
+    a = obj.T.shape[1]
+    nlv = a if nlv is None else min(nlv, a)                # :39
+    if nlv == 0:                                           # :41-45
+        X[:, :] = obj.xmeans[None, :]
+        return X
+    X = transform(obj, X, nlv=nlv) @ obj.P[:, :nlv].T      # :47-48
+    X = X / (1.0 / obj.xscales)[None, :]                   # :50 scale!(X, 1 ./ xscales) divides by its argument
+    X = X - (-obj.xmeans)[None, :]                         # :52 center!(X, -xmeans)
+    return X
+
+
+def xresid(obj, X, *, nlv=None):
+    """xfit.jl:88-99 — E = X - xfit(object, X; nlv)."""
+    X = ensure_mat(X)
+    return X - xfit(obj, X, nlv=nlv)
+
+
 # ---------------------------------------------------------------- parity aid
 def sign_align(ref, dev):
     """Per-LV signs s_a = sign(<W_ref[:,a], W_dev[:,a]>): columns a

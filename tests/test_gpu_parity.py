@@ -383,3 +383,32 @@ def test_locwlv_batched_tiny_fits(jc, q, scal, weighted):
         jc.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw, nlv=nlv)
     with pytest.raises(ValueError):
         oracle.locwlv(Xtr, Ytr, X, listnn=listnn, listw=listw, nlv=nlv)
+
+
+@pytest.mark.parametrize("scal", [False, True])
+def test_xfit_xresid(jc, scal):
+    """Next row: xfit / xresid and their bang forms (xfit.jl:33-99) for nlv = nothing, a
+    partial nlv and nlv = 0; ragged m and p so that tile edges are exercised."""
+    n, p, q, nlv, m = 700, 203, 3, 9, 333
+    X, Y = synth.synth_matrix(1, n, p), synth.synth_matrix(2, n, q)
+    w = synth.synth_weights(n, uniform=False)
+    Xn = synth.synth_matrix(4, m, p) * 3.0 + 1.0
+    fm = jc.plskern(X, Y, w, nlv=nlv, scal=scal)
+    ref = oracle.plskern(X, Y, w, nlv=nlv, scal=scal)
+    for k in (None, 4, 0, 50):
+        want = oracle.xfit(ref, Xn, nlv=k)
+        got = jc.xfit(fm, Xn, nlv=k)
+        assert got.shape == (m, p) and relerr(got, want) < 1e-10, k
+        e_want = oracle.xresid(ref, Xn, nlv=k)
+        e_got = jc.xresid(fm, Xn, nlv=k)
+        assert np.max(np.abs(e_got - e_want)) < 1e-10 * np.max(np.abs(Xn)), k
+        Z = np.asfortranarray(Xn.copy())
+        assert jc.xfit_bang(fm, Z, nlv=k) is Z and relerr(Z, want) < 1e-10
+        Z = np.asfortranarray(Xn.copy())
+        jc.xresid_bang(fm, Z, nlv=k)
+        assert np.array_equal(Z, e_got)
+    with pytest.raises(TypeError):
+        jc.xfit_bang(fm, np.ascontiguousarray(Xn))           # xfit! takes X::Matrix only
+    # full rank: the model reproduces its own training X
+    fm_full = jc.plskern(X[:40, :30], Y[:40], nlv=30)
+    assert np.max(np.abs(jc.xresid(fm_full, X[:40, :30]))) < 1e-9
