@@ -17,8 +17,10 @@
 
 namespace jcb {
 
-constexpr int LW_THREADS = 256;
+constexpr int LW_THREADS = 1024;   // one CTA per SM: 32 warps hide the L2 latency of the two slab passes per LV
 constexpr int LW_WARPS = LW_THREADS / 32;
+constexpr int LW_CG = 8;           // column groups of the t = Xs r pass (partials per group)
+constexpr int LW_RQ = LW_WARPS / LW_CG;   // row quarters
 
 struct LocwParams {
     const double* Xtr;
@@ -48,7 +50,7 @@ __device__ __forceinline__ double lw_block_sum(double v, double* red) {
     return warp_sum(t);
 }
 
-__global__ void __launch_bounds__(LW_THREADS) locw_plskern_kernel(const LocwParams prm) {
+__global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwParams prm) {
     extern __shared__ double sm[];
     const int p = prm.p, q = prm.q, kmax = prm.kmax, amax = prm.amax;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -56,8 +58,8 @@ __global__ void __launch_bounds__(LW_THREADS) locw_plskern_kernel(const LocwPara
     double* wts = sm;                    // kmax
     double* t_s = wts + kmax;            // kmax
     double* dt_s = t_s + kmax;           // kmax
-    double* tp_s = dt_s + kmax;          // LW_WARPS * kmax partial t per warp
-    double* Ys = tp_s + LW_WARPS * kmax; // kmax * q
+    double* tp_s = dt_s + kmax;          // LW_CG * kmax partial t per column group
+    double* Ys = tp_s + LW_CG * kmax;    // kmax * q
     double* xm = Ys + kmax * q;          // p
     double* xsc = xm + p;                // p
     double* w_s = xsc + p;               // p
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(LW_THREADS) locw_plskern_kernel(const LocwPara
                 ysc[c] = sc;
             }
         }
+        __syncthreads();     // the XtY accumulation below reads the centred Ys
         // ---- X: gather the neighbours' rows column by column, means, scales, centre/scale, and XtY
         for (int j = warp; j < p; j += LW_WARPS) {
             const double* src = prm.Xtr + (int64_t)j * prm.ldxt;
@@ -231,28 +234,34 @@ __global__ void __launch_bounds__(LW_THREADS) locw_plskern_kernel(const LocwPara
                 r_s[j] = rv;
             }
             __syncthreads();
-            // t = Xs r: warp w takes columns j = w, w + 8, ...; lanes over rows (coalesced); partials per warp
-            for (int r0 = 0; r0 < k; r0 += 32 * 8) {
-                double part[8];
+            // t = Xs r: warp (g, c) takes columns j = g, g + 8, ... and the 32-row blocks c, c + 4, ...;
+            // lanes over rows (coalesced); one partial vector per column group
+            {
+                const int g = warp & (LW_CG - 1), cq = warp / LW_CG;
+                for (int rb = cq * 32; rb < k; rb += 32 * LW_RQ * 4) {
+                    double part[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) part[u] = 0.0;
-                for (int j = warp; j < p; j += LW_WARPS) {
-                    const double rj = r_s[j];
-                    const double* col = Xs + (int64_t)j * k + r0 + lane;
+                    for (int u = 0; u < 4; ++u) part[u] = 0.0;
+                    const int rr = rb + lane;
+#pragma unroll 2
+                    for (int j = g; j < p; j += LW_CG) {
+                        const double rj = r_s[j];
+                        const double* col = Xs + (int64_t)j * k + rr;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (r0 + lane + 32 * u < k) part[u] += col[32 * u] * rj;
+                        for (int u = 0; u < 4; ++u)
+                            if (rr + 32 * LW_RQ * u < k) part[u] += col[32 * LW_RQ * u] * rj;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rr + 32 * LW_RQ * u < k) tp_s[g * kmax + rr + 32 * LW_RQ * u] = part[u];
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (r0 + lane + 32 * u < k) tp_s[warp * kmax + r0 + lane + 32 * u] = part[u];
             }
             __syncthreads();
             double stt = 0.0;
             for (int r = tid; r < k; r += LW_THREADS) {
                 double tv = 0.0;
 #pragma unroll
-                for (int w8 = 0; w8 < LW_WARPS; ++w8) tv += tp_s[w8 * kmax + r];
+                for (int w8 = 0; w8 < LW_CG; ++w8) tv += tp_s[w8 * kmax + r];
                 t_s[r] = tv;
                 const double d = wts[r] * tv;
                 dt_s[r] = d;
@@ -307,14 +316,14 @@ int launch_locw(Ctx* c, const double* dXtr, int64_t ldxt, const double* dYtr, in
                 double* d_pred) {
     (void)ntr;
     const int amax = std::max(1, std::min<int>(std::min<int64_t>(kmax, p), k_hi));
-    const size_t smem = (size_t)(3 * kmax + LW_WARPS * kmax + kmax * q + 5 * p + p * q + q * amax + 3 * q * q +
+    const size_t smem = (size_t)(3 * kmax + LW_CG * kmax + kmax * q + 5 * p + p * q + q * amax + 3 * q * q +
                                  4 * q + 2 * amax + 32) * 8;
     if (q > 16 || smem > 220 * 1024) {
         set_error("locw: problem too large for the batched kernel (kmax=%d p=%lld q=%lld needs %zu bytes of "
                   "shared memory, q <= 16)", kmax, (long long)p, (long long)q, smem);
         return JCB200_EINVAL;
     }
-    const int grid = (int)std::min<int64_t>(m, 2 * (int64_t)c->num_sms);
+    const int grid = (int)std::min<int64_t>(m, (int64_t)c->num_sms);
     const int64_t stride = ((int64_t)kmax * p + 2 * p * amax + 1) & ~(int64_t)1;
     JCB_TRY(ensure(c->locw_ws, (size_t)grid * stride * 8));
     LocwParams prm;

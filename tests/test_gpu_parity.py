@@ -412,3 +412,19 @@ def test_xfit_xresid(jc, scal):
     # full rank: the model reproduces its own training X
     fm_full = jc.plskern(X[:40, :30], Y[:40], nlv=30)
     assert np.max(np.abs(jc.xresid(fm_full, X[:40, :30]))) < 1e-9
+
+
+def test_locwlv_neighbourhood_sizes(jc):
+    """Neighbourhood sizes around the kernel's 32-row block edges (a missing barrier once showed only for
+    33 <= k <= 64)."""
+    rng = np.random.default_rng(11)
+    ntr, p, m, nlv = 400, 37, 6, 3
+    Xtr = synth.synth_matrix(1, ntr, p)
+    Ytr = synth.synth_matrix(2, ntr, 1) + Xtr[:, :1] * 2.0
+    X = synth.synth_matrix(4, m, p)
+    for k in (5, 31, 32, 33, 34, 63, 64, 65, 129, 257):
+        listnn = [np.sort(rng.choice(ntr, size=k, replace=False)) for _ in range(m)]
+        got = jc.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=range(0, nlv + 1)).pred
+        ref = oracle.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=range(0, nlv + 1))
+        for a in range(nlv + 1):
+            assert relerr(got[a], ref[a]) < 1e-11, (k, a)
