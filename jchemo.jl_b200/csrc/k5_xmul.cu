@@ -75,12 +75,21 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
         mu_pad[k] = k < p ? mu[k] : 0.0;
 }
 
+// the sweep epilogue (51 prefix sums and 51 x q stores per row) runs on its own warps so that it overlaps the
+// consumers' DMMA work on the next tile instead of serialising with it.  Its DFMAs queue behind the DMMAs on
+// the shared FP64 pipe (each waits about one DMMA slot), so the work is spread over as many warps as there
+// are consumers: one row per thread, every second response per warp.
+template <bool SWEEP, int NCW>
+__host__ __device__ constexpr int xm_epw() { return SWEEP ? NCW : 0; }
+
 template <int NPB, int NEX, bool SWEEP, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const XmulParams prm) {
+__global__ void __launch_bounds__((NCW + 1 + xm_epw<SWEEP, NCW>()) * 32, XM_OCC)
+xmul_kernel(const XmulParams prm) {
     constexpr int XM_NCW = NCW;
     constexpr int XM_MT = 16 * NCW;
     constexpr int XM_PITCH = XM_MT + 4;
-    constexpr int XM_THREADS = (NCW + 1) * 32;
+    constexpr int XM_EPW = xm_epw<SWEEP, NCW>();
+    constexpr int XM_THREADS = (NCW + 1 + XM_EPW) * 32;
     // NPB column blocks go through DMMA; NEX (<= 2) leftover columns are plain DFMA dot products on the
     // A fragments this lane already holds (a whole padded 8-column block for 1-2 columns would cost
     // 1/NPB more DMMA time: at nlv = 25 the score GEMM drops from 4 to 3 blocks)
@@ -97,6 +106,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const Xmul
     double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
     uint64_t* full = reinterpret_cast<uint64_t*>(cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0));
     uint64_t* empty = full + nstage;
+    uint64_t* tfull = empty + nstage;      // sweep: score tile in out_s complete (consumers -> epilogue warps)
+    uint64_t* tempty = tfull + 1;          // sweep: out_s read out (epilogue warps -> consumers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < prm.nchunk * XM_KC; k += XM_THREADS) mu_s[k] = prm.mu[k];
@@ -106,6 +117,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const Xmul
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], XM_NCW);
+        }
+        if (SWEEP) {
+            mbar_init(tfull, XM_NCW);
+            mbar_init(tempty, XM_EPW);
         }
         fence_barrier_init();
     }
@@ -156,7 +171,53 @@ __global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const Xmul
         return;
     }
 
+    if (SWEEP && warp > XM_NCW) {
+        // ------------------------------------------------------------------ sweep epilogue warps
+        // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]: one row per thread, k outer, up to 8
+        // responses carried in registers (independent chains), Cy from shared memory; a warp's store
+        // covers 32 consecutive rows of one column (256 bytes)
+        const int ew = warp - XM_NCW - 1;
+        const int r = (ew % (XM_MT / 32)) * 32 + lane;
+        const int jh = ew / (XM_MT / 32);                 // 0 / 1: even / odd responses
+        const int q = prm.q;
+        const int64_t msz = prm.m * (int64_t)q;
+        uint32_t tn = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tn) {
+            const int64_t row0 = t * XM_MT;
+            const bool rok = row0 + r < prm.m;
+            mbar_wait(tfull, tn & 1);
+            for (int j0 = jh; j0 < q; j0 += 16) {
+                double pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pv[u] = (j0 + 2 * u < q) ? prm.ymeans[j0 + 2 * u] : 0.0;
+                double* dk = prm.Pred + row0 + r + (int64_t)j0 * prm.m;
+                const double* ts = out_s + r;
+                const double* cy = cy_s + j0;
+                for (int k = 0; k <= prm.k_hi; ++k) {
+                    if (k >= prm.k_lo) {
+                        if (rok) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (j0 + 2 * u < q) __stcs(dk + (int64_t)(2 * u) * prm.m, pv[u]);
+                        }
+                        dk += msz;
+                    }
+                    if (k < prm.k_hi) {
+                        const double tv = ts[k * XM_PITCH];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j0 + 2 * u < q) pv[u] = fma(tv, cy[k * q + 2 * u], pv[u]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+        return;
+    }
+
     // ---------------------------------------------------------------------- consumers
+    uint32_t tn = 0;
     const int g = lane >> 2, kk = lane & 3;
     const int m0 = warp * 16;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -202,6 +263,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const Xmul
             if (lane == 0) mbar_arrive(&empty[buf]);
         }
         // ---- epilogue: fragments -> shared (this warp's 16 rows) -> 128-byte global rows
+        if (SWEEP && tn > 0) mbar_wait(tempty, (tn - 1) & 1);     // the previous tile has been read out
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -230,31 +292,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, XM_OCC) xmul_kernel(const Xmul
                 }
             }
         } else {
-            // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]: k outer, up to 8 responses
-            // per lane carried in registers (independent chains), Cy from shared memory
-            const int q = prm.q;
-            const int64_t msz = prm.m * (int64_t)q;
-            for (int j0 = half; j0 < q; j0 += 16) {
-                double pv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) pv[u] = (j0 + 2 * u < q) ? prm.ymeans[j0 + 2 * u] : 0.0;
-                double* dst = prm.Pred + row0 + m0 + r;
-                for (int k = 0; k <= prm.k_hi; ++k) {
-                    if (k >= prm.k_lo && rok) {
-                        double* dk = dst + (int64_t)(k - prm.k_lo) * msz;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (j0 + 2 * u < q) dk[(int64_t)(j0 + 2 * u) * prm.m] = pv[u];
-                    }
-                    if (k < prm.k_hi) {
-                        const double t = out_s[k * XM_PITCH + m0 + r];
-                        const double* cy = cy_s + k * q + j0;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (j0 + 2 * u < q) pv[u] += t * cy[2 * u];
-                    }
-                }
-            }
+            if (lane == 0) mbar_arrive(tfull);      // (after the __syncwarp above) hand the tile over
+            ++tn;
         }
         __syncwarp();
     }
@@ -274,7 +313,7 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     constexpr int NP = NPB * 8 + NEX;
     constexpr int XM_MT = 16 * NCW;
     constexpr int XM_PITCH = XM_MT + 4;
-    constexpr int XM_THREADS = (NCW + 1) * 32;
+    constexpr int XM_THREADS = (NCW + 1 + xm_epw<SWEEP, NCW>()) * 32;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
     const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
                       (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
