@@ -19,8 +19,6 @@ namespace jcb {
 
 constexpr int LW_THREADS = 1024;   // one CTA per SM: 32 warps hide the L2 latency of the two slab passes per LV
 constexpr int LW_WARPS = LW_THREADS / 32;
-constexpr int LW_CG = 8;           // column groups of the t = Xs r pass (partials per group)
-constexpr int LW_RQ = LW_WARPS / LW_CG;   // row quarters
 
 struct LocwParams {
     const double* Xtr;
@@ -34,7 +32,7 @@ struct LocwParams {
     const int64_t* nn_idx;   // concatenated neighbour rows (zero based)
     const int64_t* nn_off;   // m + 1 offsets
     const double* nn_w;      // concatenated weights or nullptr
-    int k_lo, k_hi, scal, kmax, amax;
+    int k_lo, k_hi, scal, kmax, amax, tpsz;   // kmax: even upper bound of the slab pitch; tpsz: doubles in tp_s
     double* scratch;         // per CTA: Xs kmax*p | P p*amax | R p*amax
     int64_t scratch_stride;
     double* pred;            // m x q x nk (column-major)
@@ -51,15 +49,15 @@ __device__ __forceinline__ double lw_block_sum(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwParams prm) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int p = prm.p, q = prm.q, kmax = prm.kmax, amax = prm.amax;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // shared layout
     double* wts = sm;                    // kmax
     double* t_s = wts + kmax;            // kmax
     double* dt_s = t_s + kmax;           // kmax
-    double* tp_s = dt_s + kmax;          // LW_CG * kmax partial t per column group
-    double* Ys = tp_s + LW_CG * kmax;    // kmax * q
+    double* tp_s = dt_s + kmax;          // tpsz: partial t per column group
+    double* Ys = tp_s + prm.tpsz;        // kmax * q
     double* xm = Ys + kmax * q;          // p
     double* xsc = xm + p;                // p
     double* w_s = xsc + p;               // p
@@ -83,7 +81,8 @@ __global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwP
         const int64_t o0 = prm.nn_off[i];
         const int k = (int)(prm.nn_off[i + 1] - o0);
         const int64_t* idx = prm.nn_idx + o0;
-        double* Xs = prm.scratch + (int64_t)blockIdx.x * prm.scratch_stride;     // k x p, ld = k
+        const int kp = (k + 1) & ~1;                                             // even slab pitch: 16-byte rows pairs
+        double* Xs = prm.scratch + (int64_t)blockIdx.x * prm.scratch_stride;     // k x p, ld = kp
         double* Pg = Xs + (int64_t)kmax * p;
         double* Rg = Pg + (int64_t)p * amax;
         const int a_fit = min(min(k, p), prm.k_hi);                              // plskern.jl:116
@@ -136,7 +135,8 @@ __global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwP
         // ---- X: gather the neighbours' rows column by column, means, scales, centre/scale, and XtY
         for (int j = warp; j < p; j += LW_WARPS) {
             const double* src = prm.Xtr + (int64_t)j * prm.ldxt;
-            double* col = Xs + (int64_t)j * k;
+            double* col = Xs + (int64_t)j * kp;
+            if (lane == 0 && kp > k) col[k] = 0.0;
             double a0 = 0.0;
             for (int r = lane; r < k; r += 32) {
                 const double x = src[idx[r]];
@@ -234,39 +234,41 @@ __global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwP
                 r_s[j] = rv;
             }
             __syncthreads();
-            // t = Xs r: warp (g, c) takes columns j = g, g + 8, ... and the 32-row blocks c, c + 4, ...;
-            // lanes over rows (coalesced); one partial vector per column group
+            // t = Xs r: the slab is cut into 64-row blocks (a lane holds two rows: 16-byte loads) and, when there
+            // are fewer blocks than warps, into column groups; one partial vector per column group
+            const int RB = (kp + 63) >> 6;
+            const int NCG = RB >= LW_WARPS ? 1 : LW_WARPS / RB;
             {
-                const int g = warp & (LW_CG - 1), cq = warp / LW_CG;
-                for (int rb = cq * 32; rb < k; rb += 32 * LW_RQ * 4) {
-                    double part[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) part[u] = 0.0;
-                    const int rr = rb + lane;
-#pragma unroll 2
-                    for (int j = g; j < p; j += LW_CG) {
-                        const double rj = r_s[j];
-                        const double* col = Xs + (int64_t)j * k + rr;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (rr + 32 * LW_RQ * u < k) part[u] += col[32 * LW_RQ * u] * rj;
+                const int cg = RB >= LW_WARPS ? 0 : warp / RB;
+                if (cg < NCG) {
+                    for (int rb = RB >= LW_WARPS ? warp : warp % RB; rb < RB; rb += LW_WARPS) {
+                        const int row = rb * 64 + 2 * lane;
+                        if (row < kp) {
+                            double ax = 0.0, ay = 0.0;
+                            const double* base = Xs + row;
+#pragma unroll 4
+                            for (int j = cg; j < p; j += NCG) {
+                                const double2 x = *reinterpret_cast<const double2*>(base + (int64_t)j * kp);
+                                const double rj = r_s[j];
+                                ax = fma(x.x, rj, ax);
+                                ay = fma(x.y, rj, ay);
+                            }
+                            *reinterpret_cast<double2*>(tp_s + cg * (RB * 64) + row) = make_double2(ax, ay);
+                        }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (rr + 32 * LW_RQ * u < k) tp_s[g * kmax + rr + 32 * LW_RQ * u] = part[u];
                 }
             }
             __syncthreads();
             double stt = 0.0;
             for (int r = tid; r < k; r += LW_THREADS) {
                 double tv = 0.0;
-#pragma unroll
-                for (int w8 = 0; w8 < LW_CG; ++w8) tv += tp_s[w8 * kmax + r];
+                for (int w8 = 0; w8 < NCG; ++w8) tv += tp_s[w8 * (RB * 64) + r];
                 t_s[r] = tv;
                 const double d = wts[r] * tv;
                 dt_s[r] = d;
                 stt += tv * d;
             }
+            if (tid == 0 && kp > k) dt_s[k] = 0.0;
             const double tt = lw_block_sum(stt, red);
             // c = XtY' r / tt (XtY before deflation)
             for (int c = warp; c < q; c += LW_WARPS) {
@@ -276,17 +278,44 @@ __global__ void __launch_bounds__(LW_THREADS, 1) locw_plskern_kernel(const LocwP
                 if (lane == 0) c_s[c] = tt > 0.0 ? s2 / tt : 0.0;
             }
             __syncthreads();
-            // zp = Xs'(D t); XtY -= zp c'; P_a = zp / tt; R_a = r
-            for (int j = warp; j < p; j += LW_WARPS) {
-                const double* col = Xs + (int64_t)j * k;
-                double s2 = 0.0;
-                for (int r = lane; r < k; r += 32) s2 += col[r] * dt_s[r];
-                s2 = warp_sum(s2);
-                if (lane == 0) {
-                    for (int c = 0; c < q; ++c) xty[j + c * p] -= s2 * c_s[c];
-                    Pg[j + (int64_t)a * p] = tt > 0.0 ? s2 / tt : 0.0;
-                    Rg[j + (int64_t)a * p] = r_s[j];
+            // zp = Xs'(D t): columns from the last to the first — the t pass ran first to last, so the tail of
+            // the slab is the part most likely still in L2.  A warp takes four columns at a time (16-byte loads,
+            // two rows per lane) and folds the four lane-partials with one transposing butterfly
+            for (int qd = ((p + 3) >> 2) - 1 - warp; qd >= 0; qd -= LW_WARPS) {
+                const int j0 = qd * 4;
+                const double* c0 = Xs + (int64_t)j0 * kp;
+                const double* c1 = Xs + (int64_t)min(j0 + 1, p - 1) * kp;
+                const double* c2 = Xs + (int64_t)min(j0 + 2, p - 1) * kp;
+                const double* c3 = Xs + (int64_t)min(j0 + 3, p - 1) * kp;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int row = 2 * lane; row < kp; row += 64) {
+                    const double2 d = *reinterpret_cast<const double2*>(dt_s + row);
+                    const double2 x0 = *reinterpret_cast<const double2*>(c0 + row);
+                    const double2 x1 = *reinterpret_cast<const double2*>(c1 + row);
+                    const double2 x2 = *reinterpret_cast<const double2*>(c2 + row);
+                    const double2 x3 = *reinterpret_cast<const double2*>(c3 + row);
+                    a0 = fma(x0.y, d.y, fma(x0.x, d.x, a0));
+                    a1 = fma(x1.y, d.y, fma(x1.x, d.x, a1));
+                    a2 = fma(x2.y, d.y, fma(x2.x, d.x, a2));
+                    a3 = fma(x3.y, d.y, fma(x3.x, d.x, a3));
                 }
+                const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+                double k0 = (h16 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, h16 ? a0 : a2, 16);
+                double k1 = (h16 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, h16 ? a1 : a3, 16);
+                double kk = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+                kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+                kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+                kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+                // lanes 0-7 hold column j0, 8-15 j0 + 1, 16-23 j0 + 2, 24-31 j0 + 3
+                if ((lane & 7) == 0 && j0 + (lane >> 3) < p) zp_s[j0 + (lane >> 3)] = kk;
+            }
+            __syncthreads();
+            // XtY -= zp c'; P_a = zp / tt; R_a = r
+            for (int j = tid; j < p; j += LW_THREADS) {
+                const double z = zp_s[j];
+                for (int c = 0; c < q; ++c) xty[j + c * p] -= z * c_s[c];
+                Pg[j + (int64_t)a * p] = tt > 0.0 ? z / tt : 0.0;
+                Rg[j + (int64_t)a * p] = r_s[j];
             }
             for (int c = tid; c < q; c += LW_THREADS) C_s[c + a * q] = c_s[c];
             __syncthreads();
@@ -315,8 +344,10 @@ int launch_locw(Ctx* c, const double* dXtr, int64_t ldxt, const double* dYtr, in
                 const int64_t* d_off, const double* d_w, int kmax, int k_lo, int k_hi, int scal,
                 double* d_pred) {
     (void)ntr;
+    kmax = (kmax + 1) & ~1;                                   // even slab pitch and shared-memory strides
+    const int tpsz = std::max(kmax, LW_WARPS * 64);
     const int amax = std::max(1, std::min<int>(std::min<int64_t>(kmax, p), k_hi));
-    const size_t smem = (size_t)(3 * kmax + LW_CG * kmax + kmax * q + 5 * p + p * q + q * amax + 3 * q * q +
+    const size_t smem = (size_t)(3 * kmax + tpsz + kmax * q + 5 * p + p * q + q * amax + 3 * q * q +
                                  4 * q + 2 * amax + 32) * 8;
     if (q > 16 || smem > 220 * 1024) {
         set_error("locw: problem too large for the batched kernel (kmax=%d p=%lld q=%lld needs %zu bytes of "
@@ -329,7 +360,7 @@ int launch_locw(Ctx* c, const double* dXtr, int64_t ldxt, const double* dYtr, in
     LocwParams prm;
     prm.Xtr = dXtr; prm.ldxt = ldxt; prm.Ytr = dYtr; prm.ldyt = ldyt; prm.X = dX; prm.ldx = ldx; prm.m = m;
     prm.p = (int)p; prm.q = (int)q; prm.nn_idx = d_idx; prm.nn_off = d_off; prm.nn_w = d_w;
-    prm.k_lo = k_lo; prm.k_hi = k_hi; prm.scal = scal; prm.kmax = kmax; prm.amax = amax;
+    prm.k_lo = k_lo; prm.k_hi = k_hi; prm.scal = scal; prm.kmax = kmax; prm.amax = amax; prm.tpsz = tpsz;
     prm.scratch = (double*)c->locw_ws.p; prm.scratch_stride = stride; prm.pred = d_pred;
     JCB_CUDA(cudaFuncSetAttribute(locw_plskern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     locw_plskern_kernel<<<grid, LW_THREADS, smem, c->stream>>>(prm);
