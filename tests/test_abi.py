@@ -65,3 +65,43 @@ def test_argument_validation_shapes():
         jchemo_b200.plskern(np.zeros((5, 2)), np.zeros((4, 1)), nlv=1)
     with pytest.raises(TypeError):
         jchemo_b200.plskern_bang(np.zeros((5, 2), order="C"), np.zeros((5, 1), order="F"), nlv=1)
+
+
+def test_next_row_host_logic_without_gpu():
+    """Host-side checks of the next-row mirrors that fire before any device call."""
+    import jchemo_b200 as jc
+    import oracle
+    rng = np.random.default_rng(0)
+    Xtr, Ytr, X = rng.random((30, 6)), rng.random((30, 1)), rng.random((3, 6))
+    listnn = [np.arange(10), np.arange(3), np.arange(5, 20)]
+    # a neighbourhood smaller than nlv throws in the reference (locwlv.jl:37); so do the oracle and the mirror
+    with pytest.raises(ValueError):
+        jc.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=5)
+    with pytest.raises(ValueError):
+        oracle.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=5)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        jc.locwlv(Xtr, Ytr, X[:, :4], listnn=listnn, nlv=2)
+    with pytest.raises(TypeError):
+        jc.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=2, fun=oracle.plskern)
+    fm = oracle.plskern(Xtr, Ytr, nlv=3)
+    with pytest.raises(TypeError):
+        jc.xfit_bang(fm, np.ascontiguousarray(rng.random((4, 6))))
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        jc.xresid(fm, rng.random((4, 5)))
+
+
+def test_oracle_xfit_and_locwlv_properties():
+    """xfit at full rank reproduces X; xresid + xfit == X; locwlv with every row as neighbour and unit weights
+    equals one global fit."""
+    import oracle
+    rng = np.random.default_rng(1)
+    X, Y = rng.random((12, 5)), rng.random((12, 2))
+    fm = oracle.plskern(X, Y, nlv=5)
+    assert np.allclose(oracle.xfit(fm, X), X, atol=1e-10)
+    assert np.allclose(oracle.xfit(fm, X, nlv=0), np.tile(fm.xmeans, (12, 1)))
+    assert np.allclose(oracle.xfit(fm, X, nlv=2) + oracle.xresid(fm, X, nlv=2), X)
+    Xq = rng.random((4, 5))
+    loc = oracle.locwlv(X, Y, Xq, listnn=[np.arange(12)] * 4, nlv=range(0, 4))
+    glob = oracle.predict(oracle.plskern(X, Y, nlv=3), Xq, nlv=range(0, 4))
+    for a in range(4):
+        assert np.allclose(loc[a], glob[a], atol=1e-12)
