@@ -13,7 +13,8 @@ constexpr int XF_MT = 128;    // rows per CTA tile
 constexpr int XF_NT = 64;     // columns per CTA tile
 constexpr int XF_KC = 32;     // LVs per staged chunk
 
-// thread (tx = tid & 15, ty = tid >> 4): rows 8 tx .. 8 tx + 7, columns 4 ty .. 4 ty + 3 of the tile
+// thread (tx = tid & 15, ty = tid >> 4): row pairs 32 i + 2 tx (+1), i = 0..3, columns 4 ty .. 4 ty + 3 of the
+// tile — a half-warp's 16-byte stores to one column cover 256 contiguous bytes
 __global__ void __launch_bounds__(256) xfit_kernel(double* __restrict__ X, int64_t ldx, int64_t m, int p,
                                                    const double* __restrict__ T, int64_t ldt,
                                                    const double* __restrict__ P, int64_t ldp, int nlv,
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) xfit_kernel(double* __restrict__ X, int64
             double tv[8], pv[4];
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&Ts[k][8 * tx + i]);
+                const double2 v = *reinterpret_cast<const double2*>(&Ts[k][16 * i + 2 * tx]);
                 tv[i] = v.x;
                 tv[i + 1] = v.y;
             }
@@ -66,12 +67,25 @@ __global__ void __launch_bounds__(256) xfit_kernel(double* __restrict__ X, int64
         const int col = c0 + 4 * ty + j;
         if (col >= p) continue;
         const double mu = xm[col], sc = xs[col];
-        double* dst = X + (int64_t)col * ldx + r0 + 8 * tx;
+        double* dcol = X + (int64_t)col * ldx + r0 + 2 * tx;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (r0 + 8 * tx + i >= m) break;
-            const double fit = acc[j][i] * sc + mu;      // scale!(X, 1 ./ xscales); center!(X, -xmeans)
-            dst[i] = resid ? dst[i] - fit : fit;         // xresid: X .- xfit(...)
+        for (int i = 0; i < 8; i += 2) {
+            const int64_t row = r0 + 16 * i + 2 * tx;
+            if (row >= m) break;
+            double* dst = dcol + 16 * i;
+            // scale!(X, 1 ./ xscales); center!(X, -xmeans); xresid: X .- xfit(...)
+            const double f0 = acc[j][i] * sc + mu, f1 = acc[j][i + 1] * sc + mu;
+            if (row + 1 < m) {
+                double2 v = make_double2(f0, f1);
+                if (resid) {
+                    const double2 x = *reinterpret_cast<const double2*>(dst);
+                    v.x = x.x - f0;
+                    v.y = x.y - f1;
+                }
+                *reinterpret_cast<double2*>(dst) = v;
+            } else {
+                dst[0] = resid ? dst[0] - f0 : f0;
+            }
         }
     }
 }

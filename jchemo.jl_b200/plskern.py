@@ -146,7 +146,7 @@ def transform(obj, X, *, nlv=None):
     if p != obj.R.shape[0]:
         raise ValueError(f"DimensionMismatch: X has {p} columns, the model has {obj.R.shape[0]}")
     nlv = max(nlv, 0)
-    T = np.empty((m, nlv), order="F")
+    T = _out_empty((m, nlv))
     if nlv > 0 and m > 0:
         R = np.asfortranarray(obj.R)
         rc = _lib.lib().jcb200_transform(_ptr(X), _ld(X), m, p, _ptr(obj.xmeans), _ptr(obj.xscales),
