@@ -11,99 +11,118 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Dominant eigenvector of the symmetric PSD Q x Q matrix M by repeated squaring, ONE warp, compile-time Q
-// (all loops unrolled, no integer division, no block barrier).  L = 32/Q lanes share row i; a lane owns
-// the entries (i, jl + u*L).  A <- A*A (A symmetric: column j = row j, both operands contiguous rows)
-// converges quadratically to a multiple of v v'.  The matrix is renormalised by its trace every third
-// squaring, where convergence is checked: if the normalised matrix moved by < 1e-4 over the last three
-// squarings, the contamination three squarings ago was <~ 1e-4 and is now its 8th power.
-// Result: column `best` (largest diagonal) of the converged matrix in v_out[0..Q).
+// (all loops unrolled, no integer division, no block barrier, no shuffles).  A <- A*A (A symmetric:
+// column j = row j, both operands contiguous rows) converges quadratically to a multiple of v v'.
+//  * Only the upper triangle is computed: the NT = Q(Q+1)/2 entries are dealt round-robin to the lanes
+//    (lane l owns entries l, l+32, ...), each entry is one row-by-row dot (two FMA chains, 16-byte loads
+//    when Q is even and the buffers are aligned) and is stored to both (i,j) and (j,i).
+//  * After every squaring every lane reads the Q diagonal entries itself and adds them in the same order,
+//    so the trace tau is known to all lanes without a reduction.  The next squaring is scaled by the power
+//    of two 2^(-2 e), e = exponent(tau): exact, no division, trace stays O(1).
+//  * Convergence: tr(A^2)/tr(A)^2 = 1 - 2 rho + O(rho^2), rho = (lambda_2/lambda_1)^(2^k) the remaining
+//    contamination.  When a squaring shows rho < 5e-5, its result carries rho^2 and ONE more squaring
+//    leaves rho^4 < 1e-17: the trace of a matrix is taken inside the squaring that consumes it, and the
+//    test on it ends the loop right after that squaring.
+// Result: column `best` (largest diagonal) of the converged matrix in v_out[0..Q); M = 0 gives e_1.
 template <int Q>
 __device__ __forceinline__ void eig_dominant_warp(const double* __restrict__ M_s, double* __restrict__ bufA,
                                                   double* __restrict__ bufB, double* __restrict__ v_out,
                                                   const int lane) {
-    constexpr int L = 32 / Q;
-    constexpr int NJ = (Q + L - 1) / L;
-    const int i = lane / L, jl = lane - i * L;
-    const bool act = i < Q;
+    constexpr int NT = Q * (Q + 1) / 2;
+    constexpr int NE = (NT + 31) / 32;
+    int ei[NE], ej[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        int rem = lane + 32 * u, i = 0;
+        if (rem >= NT) rem = NT - 1;                  // idle slot: recompute the last entry (same value)
+        while (rem >= Q - i) { rem -= Q - i; ++i; }
+        ei[u] = i;
+        ej[u] = i + rem;
+    }
     double tr = 0.0;
 #pragma unroll
     for (int d = 0; d < Q; ++d) tr += M_s[d * Q + d];
+    if (!(tr > 0.0)) {
+        if (lane < Q) v_out[lane] = (lane == 0) ? 1.0 : 0.0;
+        __syncwarp();
+        return;
+    }
     const double itr = 1.0 / tr;
-    double prev[NJ];
+    for (int e = lane; e < Q * Q; e += 32) bufA[e] = M_s[e] * itr;
+    __syncwarp();
     double* cur = bufA;
     double* nxt = bufB;
+    const bool vec = (Q % 2 == 0) &&
+                     (((unsigned long long)(uintptr_t)bufA | (unsigned long long)(uintptr_t)bufB) & 15ull) == 0ull;
+    // Warps issue in order: the trace of the CURRENT matrix is taken inside the squaring that consumes it
+    // (diagonal loads issued with the row loads, a 4-level add tree that runs beside the FMA chains, the
+    // scale applied as the last multiply), so neither the trace nor the test adds to the critical path.
+    double tau_prev = 1.0, scl_prev = 1.0;
+    for (int iter = 0; iter < 64; ++iter) {
+        double dg[Q];
 #pragma unroll
-    for (int u = 0; u < NJ; ++u) {
-        const int j = jl + u * L;
-        prev[u] = 0.0;
-        if (act && j < Q) {
-            prev[u] = M_s[i * Q + j] * itr;
-            cur[i * Q + j] = prev[u];
-        }
-    }
-    __syncwarp();
-    for (int iter = 0; iter < 90; ++iter) {
-        double acc[NJ];
+        for (int d = 0; d < Q; ++d) dg[d] = cur[d * Q + d];
+        double acc[NE][2];
 #pragma unroll
-        for (int u = 0; u < NJ; ++u) acc[u] = 0.0;
-        if (act) {
+        for (int u = 0; u < NE; ++u) {
+            const double* ri = cur + ei[u] * Q;
+            const double* rj = cur + ej[u] * Q;
+            double s0 = 0.0, s1 = 0.0;
+            if (vec) {
+                const double2* a2 = reinterpret_cast<const double2*>(ri);
+                const double2* b2 = reinterpret_cast<const double2*>(rj);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) {
-                const double aik = cur[i * Q + k];
-#pragma unroll
-                for (int u = 0; u < NJ; ++u) {
-                    const int j = jl + u * L;
-                    if (j < Q) acc[u] += aik * cur[j * Q + k];
+                for (int k = 0; k < Q / 2; ++k) {
+                    const double2 x = a2[k], y = b2[k];
+                    s0 += x.x * y.x;
+                    s1 += x.y * y.y;
                 }
-            }
-        }
-        if (iter % 3 != 2) {
-            if (act) {
+            } else {
 #pragma unroll
-                for (int u = 0; u < NJ; ++u) {
-                    const int j = jl + u * L;
-                    if (j < Q) nxt[i * Q + j] = acc[u];
+                for (int k = 0; k + 1 < Q; k += 2) {
+                    s0 += ri[k] * rj[k];
+                    s1 += ri[k + 1] * rj[k + 1];
                 }
+                if (Q & 1) s0 += ri[Q - 1] * rj[Q - 1];
             }
-            __syncwarp();
-        } else {
-            // trace of the new matrix = sum of its diagonal entries: collect them through a shuffle sum
-            double dg = 0.0;
-#pragma unroll
-            for (int u = 0; u < NJ; ++u) {
-                const int j = jl + u * L;
-                if (act && j == i) dg = acc[u];
-            }
-            const double inv = 1.0 / warp_sum(dg);
-            double chg = 0.0;
-#pragma unroll
-            for (int u = 0; u < NJ; ++u) {
-                const int j = jl + u * L;
-                if (act && j < Q) {
-                    const double nv = acc[u] * inv;
-                    chg = fmax(chg, fabs(nv - prev[u]));
-                    prev[u] = nv;
-                    nxt[i * Q + j] = nv;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) chg = fmax(chg, __shfl_xor_sync(0xffffffffu, chg, o));
-            __syncwarp();
-            if (chg < 1e-4) {
-                cur = nxt;
-                break;
-            }
+            acc[u][0] = s0;
+            acc[u][1] = s1;
         }
+        // tau = trace(cur): pairwise tree, same order in every lane
+#pragma unroll
+        for (int w2 = 1; w2 < Q; w2 <<= 1) {
+#pragma unroll
+            for (int d = 0; d + w2 < Q; d += 2 * w2) dg[d] += dg[d + w2];
+        }
+        const double tau = dg[0];
+        // scl = 2^(-2 e) with tau = f * 2^e, f in [1, 2)
+        const int ex = ((__double2hiint(tau) >> 20) & 0x7ff) - 1023;
+        const double scl = __hiloint2double((1023 - 2 * ex) << 20, 0);
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+            const double val = (acc[u][0] + acc[u][1]) * scl;
+            nxt[ei[u] * Q + ej[u]] = val;
+            nxt[ej[u] * Q + ei[u]] = val;
+        }
+        __syncwarp();
         double* t = cur;
         cur = nxt;
         nxt = t;
+        // tau / (scl_prev tau_prev^2) = tr(A_{k-1}^2)/tr(A_{k-1})^2 = 1 - 2 rho_{k-1}: rho_{k-1} < 5e-5 means the
+        // matrix just squared carried rho^2 and the one just stored carries rho^4 < 1e-17
+        if (iter > 0 && tau >= (1.0 - 1e-4) * scl_prev * tau_prev * tau_prev) break;
+        tau_prev = tau;
+        scl_prev = scl;
     }
-    __syncwarp();
     int best = 0;
+    double bd = cur[0];
 #pragma unroll
-    for (int d = 1; d < Q; ++d)
-        if (cur[d * Q + d] > cur[best * Q + best]) best = d;
+    for (int d = 1; d < Q; ++d) {
+        const double x = cur[d * Q + d];
+        if (x > bd) { bd = x; best = d; }
+    }
     if (lane < Q) v_out[lane] = cur[lane * Q + best];
+    __syncwarp();
 }
 
 // dispatch on the runtime q (2..16); executed by one full warp

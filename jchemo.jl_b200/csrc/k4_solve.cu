@@ -125,7 +125,8 @@ struct LvParams {
     do {                                                                    \
         if (rank == 0 && tid == 0 && prm.trace) {                           \
             const long long _t = clock64();                                 \
-            prm.trace[idx] += _t - tmark;                                   \
+            atomicAdd((unsigned long long*)&prm.trace[idx],                 \
+                      (unsigned long long)(_t - tmark)); /* RED: no stall */ \
             tmark = _t;                                                     \
         }                                                                   \
     } while (0)
@@ -133,22 +134,50 @@ struct LvParams {
 #define LV_MARK(idx) do { } while (0)
 #endif
 
-// dot of a shared vector with a global column, lanes strided, 8 independent loads in flight
+// dot of a shared vector with a global column, lanes strided, 8 independent loads in flight.  The
+// ragged last chunk is PREDICATED, not peeled: a peeled remainder loop splits the warp (p = 500: lanes
+// 20..31 fell out of the vector path) and serialises up to eight L2 round trips behind each other.
 __device__ __forceinline__ double warp_dot_gs(const double* __restrict__ gcol,
                                               const double* __restrict__ svec, int p, int lane) {
     double s[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) s[u] = 0.0;
-    int k = lane;
-    for (; k + 7 * 32 < p; k += 8 * 32) {
+    for (int k0 = lane; k0 < p; k0 += 8 * 32) {
         double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(gcol + k + u * 32);
+        for (int u = 0; u < 8; ++u) v[u] = (k0 + u * 32 < p) ? __ldcg(gcol + k0 + u * 32) : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += v[u] * svec[k + u * 32];
+        for (int u = 0; u < 8; ++u) s[u] += v[u] * svec[min(k0 + u * 32, p - 1)];
     }
-    for (; k < p; k += 32) s[0] += __ldcg(gcol + k) * svec[k];
     return warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+}
+
+// two global columns against one shared vector: 16 loads in flight per lane (colB may be null)
+__device__ __forceinline__ void warp_dot2_gs(const double* __restrict__ colA,
+                                             const double* __restrict__ colB,
+                                             const double* __restrict__ svec, int p, int lane,
+                                             double& outA, double& outB) {
+    double s[8], t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = t[u] = 0.0;
+    const bool hasA = colA != nullptr, hasB = colB != nullptr;
+    for (int k0 = lane; k0 < p; k0 += 8 * 32) {
+        double v[8], v2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = k0 + u * 32 < p;
+            v[u] = (in && hasA) ? __ldcg(colA + k0 + u * 32) : 0.0;
+            v2[u] = (in && hasB) ? __ldcg(colB + k0 + u * 32) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double x = svec[min(k0 + u * 32, p - 1)];
+            s[u] += v[u] * x;
+            t[u] += v2[u] * x;
+        }
+    }
+    outA = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+    outB = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
 }
 
 __device__ __forceinline__ double warp_dot_ss(const double* __restrict__ a,
@@ -364,15 +393,14 @@ lvloop_kernel(const LvParams prm) {
         __syncthreads();
         for (int k = tid; k < p; k += LV_THREADS) {
             double rv = w_s[k];
-            int j = 0;
-            for (; j + 8 <= a; j += 8) {
+            for (int j = 0; j < a; j += 8) {              // ragged last batch predicated
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldcg(Rr + k + (int64_t)(j + u) * P64);
+                for (int u = 0; u < 8; ++u)
+                    v[u] = (j + u < a) ? __ldcg(Rr + k + (int64_t)(j + u) * P64) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) rv -= d_s[j + u] * v[u];
+                for (int u = 0; u < 8; ++u) rv -= d_s[min(j + u, a - 1)] * v[u];
             }
-            for (; j < a; ++j) rv -= d_s[j] * __ldcg(Rr + k + (int64_t)j * P64);
             r_s[k] = rv;
         }
         __syncthreads();
@@ -388,24 +416,20 @@ lvloop_kernel(const LvParams prm) {
             double s[8], t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) s[u] = t[u] = 0.0;
-            int k = lane;
-            for (; k + 7 * 32 < p; k += 8 * 32) {
+            for (int k = lane; k < p; k += 8 * 32) {      // ragged last chunk predicated (see warp_dot_gs)
                 double v[8], v2[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    v[u] = row[k + u * 32];
-                    v2[u] = row2[k + u * 32];
+                    const bool in = k + u * 32 < p;
+                    v[u] = in ? row[k + u * 32] : 0.0;
+                    v2[u] = in ? row2[k + u * 32] : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const double rk = r_s[k + u * 32];
+                    const double rk = r_s[min(k + u * 32, p - 1)];
                     s[u] += v[u] * rk;
                     t[u] += v2[u] * rk;
                 }
-            }
-            for (; k < p; k += 32) {
-                s[0] += row[k] * r_s[k];
-                t[0] += row2[k] * r_s[k];
             }
             const double z1 = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
             const double z2 = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
@@ -479,6 +503,388 @@ lvloop_kernel(const LvParams prm) {
     }
 }
 
+
+// ----------------------------------------------------------------------------------------- K4, distributed form
+// The same recurrences on ONE NON-PORTABLE CLUSTER OF 16 CTAs (every B200 GPC has >= 16 SMs), with every
+// p-vector and p-row matrix SLICED over the CTAs (CTA c owns rows [c*per, (c+1)*per) of XtY, P, R, w, r,
+// zp and of the symmetric XtX) and all of it resident in shared memory; used whenever q <= 16.
+// Nothing is recomputed redundantly except the q x q eigenproblem, and nothing but the XtX slice of a
+// large p is read from L2 inside the loop.  Four small all-to-all exchanges through DISTRIBUTED SHARED
+// MEMORY per LV (each CTA stores its partial into slot [rank] of every CTA's buffer with st.async, which
+// counts the bytes on the RECEIVER's mbarrier: no cluster barrier inside the loop, a CTA goes on as soon
+// as its own 16 slots are full; every CTA sums the slots in the same fixed order, so all CTAs hold
+// bit-identical values):
+//   A  partial M = XtY_c' XtY_c (upper triangle)            -> M, then v = dominant eigenvector (every CTA)
+//   B  partial d~ = P_c' w~_c and |w~_c|^2, w~ = XtY v       -> d~, nrm   (w is normalised together with r)
+//   C  r_c = (w~_c - R_c d~)/nrm all-gathered, partial u = XtY_c' r_c
+//   D  zp_c = XtX[c,:] r (XtX slice in shared memory when GS), per-warp partials of tt = r'zp
+// then c = u/tt, P_c = zp_c/tt, XtY_c -= zp_c c' locally.  Buffers and barriers need no double-buffering:
+// a CTA can only send exchange k+1 after it has completed exchange k, which needs every peer's part of k,
+// which each peer sends (behind a block barrier) after it has consumed its buffer of exchange k-1.
+constexpr int LV16_CLUSTER = 16;
+
+struct LvdLayout {
+    int pe, sp, xs, Ps, Rs, w, r, zp, rfull, exA, exB, exU, exD, M, A, B, v, c, d, g, total;   // doubles
+};
+__host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, bool gs) {
+    LvdLayout L;
+    auto ev = [](int x) { return (x + 1) & ~1; };
+    const int nt = q * (q + 1) / 2;
+    L.pe = ev(p);
+    L.sp = per | 1;                       // odd pitch: columns of a slice fall into different banks
+    int o = 0;
+    L.rfull = o; o += L.pe + 2;           // first: 16-byte aligned for the double2 matvec
+    L.xs = o; o += ev(q * L.sp);
+    L.Ps = o; o += ev(nlv * L.sp);
+    L.Rs = o; o += ev(nlv * L.sp);
+    L.w = o; o += ev(L.sp);
+    L.r = o; o += ev(L.sp);
+    L.zp = o; o += ev(L.sp);
+    L.exA = o; o += ev(LV16_CLUSTER * nt);
+    L.exB = o; o += ev(LV16_CLUSTER * (nlv + 1));
+    L.exU = o; o += ev(LV16_CLUSTER * q);
+    L.exD = o; o += LV16_CLUSTER * 16;
+    L.M = o; o += ev(q * q);
+    L.A = o; o += ev(q * q);
+    L.B = o; o += ev(q * q);
+    L.v = o; o += ev(q);
+    L.c = o; o += ev(q);
+    L.d = o; o += ev(nlv + 1);
+    L.g = o; o += gs ? per * L.pe : 0;
+    L.total = o;
+    return L;
+}
+
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// 8-byte store into a peer CTA's shared memory that completes 8 tx-bytes on the PEER's mbarrier: the
+// receiver learns that the data has landed by waiting on its own barrier (one-way latency, no cluster
+// barrier, no release fence on the sender)
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+                 "l"(__double_as_longlong(v)), "r"(rbar)
+                 : "memory");
+}
+
+template <bool GS>
+__global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams prm) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) uint64_t bars[5];          // A, B, C, D, B2 (the rare w = e_1 redo)
+    const int p = prm.p, q = prm.q, nlv = prm.nlv;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = LV_THREADS >> 5;
+    const int rank = (int)cluster.block_rank();
+    constexpr int ncta = LV16_CLUSTER;
+    const int per = (p + ncta - 1) / ncta;
+    const int lo = min(p, rank * per), hi = min(p, lo + per), nsl = hi - lo;
+    const LvdLayout L = lvd_layout(p, q, nlv, per, GS);
+    const int pe = L.pe, sp = L.sp, nt = q * (q + 1) / 2, nd = nlv + 1;
+    double* rfull = sm + L.rfull;
+    double* xs = sm + L.xs;
+    double* Ps = sm + L.Ps;
+    double* Rs = sm + L.Rs;
+    double* w_s = sm + L.w;
+    double* r_s = sm + L.r;
+    double* zp_s = sm + L.zp;
+    double* exA = sm + L.exA;
+    double* exB = sm + L.exB;
+    double* exU = sm + L.exU;
+    double* exD = sm + L.exD;
+    double* M_s = sm + L.M;
+    double* A_s = sm + L.A;
+    double* B_s = sm + L.B;
+    double* v_s = sm + L.v;
+    double* c_s = sm + L.c;
+    double* d_s = sm + L.d;
+    double* g_s = sm + L.g;
+    const int64_t P64 = p;
+    const uint32_t barA = smem_u32(&bars[0]), barB = smem_u32(&bars[1]), barC = smem_u32(&bars[2]),
+                   barD = smem_u32(&bars[3]), barB2 = smem_u32(&bars[4]);
+    const uint32_t bytesA = (uint32_t)(ncta * nt * 8), bytesC = (uint32_t)((p + ncta * q) * 8),
+                   bytesD = (uint32_t)(ncta * 16 * 8);
+
+    if (tid == 0) {
+        for (int b = 0; b < 5; ++b) mbar_init(&bars[b], 1);
+        fence_barrier_init();
+        // arm LV 0 (a peer's data may arrive before the arming of a phase: the pending arrival keeps it open)
+        if (q > 1) mbar_arrive_expect_tx(&bars[0], bytesA);
+        mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * 8));
+        mbar_arrive_expect_tx(&bars[2], bytesC);
+        mbar_arrive_expect_tx(&bars[3], bytesD);
+    }
+    for (int e = tid; e < nsl * q; e += LV_THREADS) {
+        const int j = e / nsl, i = e - j * nsl;
+        xs[j * sp + i] = prm.XtY[lo + i + (int64_t)j * P64];
+    }
+    for (int e = p + tid; e < pe + 2; e += LV_THREADS) rfull[e] = 0.0;   // pad read by the 16-byte loop
+    if (GS) {
+        // row i of the symmetric XtX == column i: contiguous, coalesced
+        for (int e = tid; e < nsl * pe; e += LV_THREADS) {
+            const int rr = e / pe, k = e - rr * pe;
+            g_s[e] = (k < p) ? prm.XtX[(int64_t)(lo + rr) * P64 + k] : 0.0;
+        }
+    }
+    // triangle index -> (i <= j) for the M exchange
+    int ti = 0, tj = 0;
+    if (tid < nt) {
+        int rem = tid;
+        while (rem >= q - ti) { rem -= q - ti; ++ti; }
+        tj = ti + rem;
+    }
+    int nB2 = 0;        // completed phases of the redo barrier
+    __syncthreads();
+    cluster.sync();     // every CTA is running and its barriers are initialised before the first remote store
+
+    // partial dots of the w~ slice with the P slice columns j < a and with itself (j == a), sent to slot
+    // [rank] of every CTA's exB, signalling `bar` there
+    auto dots_and_send = [&](const int a, const uint32_t bar) {
+        for (int j0 = warp; j0 <= a; j0 += 4 * nwarp) {
+            double acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * nwarp;
+                const double* col = (j < a) ? Ps + j * sp : w_s;       // j == a: the norm
+                double s = 0.0;
+                if (j <= a)
+                    for (int i = lane; i < nsl; i += 32) s += col[i] * w_s[i];
+                acc[u] = s;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            }
+            if (lane < ncta) {
+                const uint32_t rb = mapa_u32(bar, lane);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u * nwarp <= a)
+                        st_async_f64(mapa_u32(smem_u32(exB + rank * nd + j0 + u * nwarp), lane), acc[u], rb);
+            }
+        }
+    };
+
+#ifdef JCB_K1_TRACE
+    long long tmark = clock64();
+#endif
+    for (int a = 0; a < nlv; ++a) {
+        const uint32_t par = a & 1;
+        const bool more = a + 1 < nlv;
+        LV_MARK(9);
+        // ---------------------------------------------------------------- A: M = XtY'XtY, v
+        if (q > 1) {
+            if (tid < nt) {
+                const double* ci = xs + ti * sp;
+                const double* cj = xs + tj * sp;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int k = 0;
+                for (; k + 3 < nsl; k += 4) {
+                    s0 += ci[k] * cj[k];
+                    s1 += ci[k + 1] * cj[k + 1];
+                    s2 += ci[k + 2] * cj[k + 2];
+                    s3 += ci[k + 3] * cj[k + 3];
+                }
+                for (; k < nsl; ++k) s0 += ci[k] * cj[k];
+                const double val = (s0 + s1) + (s2 + s3);
+                const uint32_t dst = smem_u32(exA + rank * nt + tid);
+#pragma unroll
+                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barA, cta));
+                mbar_wait(&bars[0], par);
+                if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], bytesA);
+                double v[ncta];
+#pragma unroll
+                for (int cta = 0; cta < ncta; ++cta) v[cta] = exA[cta * nt + tid];
+                double s = 0.0;
+#pragma unroll
+                for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+                M_s[ti * q + tj] = s;
+                M_s[tj * q + ti] = s;
+            }
+            __syncthreads();
+            LV_MARK(0);
+            if (warp == 0) eig_dominant_warp_q(q, M_s, A_s, B_s, v_s, lane);
+            __syncthreads();
+            LV_MARK(1);
+        }
+        // ---------------------------------------------------------------- B: w~ slice, dots d~ = P'w~, |w~|^2
+        if (tid < nsl) {
+            double t = xs[tid];
+            if (q > 1) {
+                t = 0.0;
+                for (int j = 0; j < q; ++j) t += xs[j * sp + tid] * v_s[j];
+            }
+            w_s[tid] = t;
+        }
+        __syncthreads();
+        dots_and_send(a, barB);
+        if (tid <= a) {
+            mbar_wait(&bars[1], par);
+            if (tid == 0 && more) mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * (a + 2) * 8));
+            double v[ncta];
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) v[cta] = exB[cta * nd + tid];
+            double s = 0.0;
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+            d_s[tid] = s;
+        }
+        __syncthreads();
+        if (!(d_s[a] > 0.0)) {
+            // XtY == 0 (e.g. constant Y): LAPACK's svd of a zero matrix returns U = I, so the reference
+            // takes w = e_1 (plskern.jl:154) and carries on with c = 0.  Redo the dots on e_1 (all CTAs
+            // take this branch together: d_s is bit-identical everywhere).
+            cluster.sync();      // peers have finished reading the first pass out of their exB
+            if (tid == 0) mbar_arrive_expect_tx(&bars[4], (uint32_t)(ncta * (a + 1) * 8));
+            if (tid < nsl) w_s[tid] = (lo + tid == 0) ? 1.0 : 0.0;
+            __syncthreads();
+            dots_and_send(a, barB2);
+            if (tid <= a) {
+                mbar_wait(&bars[4], nB2 & 1);
+                double s = 0.0;
+                for (int cta = 0; cta < ncta; ++cta) s += exB[cta * nd + tid];
+                d_s[tid] = s;
+            }
+            ++nB2;
+            __syncthreads();
+        }
+        LV_MARK(3);
+        // ---------------------------------------------------------------- C: r slice -> all CTAs, partial u
+        {
+            const double nrm = sqrt(d_s[a]);
+            if (tid < nsl) {
+                const double wv = w_s[tid];
+                double r0 = wv, r1 = 0.0;
+                int j = 0;
+                for (; j + 1 < a; j += 2) {
+                    r0 -= d_s[j] * Rs[j * sp + tid];
+                    r1 -= d_s[j + 1] * Rs[(j + 1) * sp + tid];
+                }
+                if (j < a) r0 -= d_s[j] * Rs[j * sp + tid];
+                w_s[tid] = wv / nrm;
+                r_s[tid] = (r0 + r1) / nrm;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nsl * ncta; e += LV_THREADS) {
+            const int cta = e / nsl, i = e - cta * nsl;
+            st_async_f64(mapa_u32(smem_u32(rfull + lo + i), cta), r_s[i], mapa_u32(barC, cta));
+        }
+        for (int j = warp; j < q; j += nwarp) {
+            double s = 0.0;
+            for (int i = lane; i < nsl; i += 32) s += xs[j * sp + i] * r_s[i];
+            s = warp_sum(s);
+            if (lane < ncta) st_async_f64(mapa_u32(smem_u32(exU + rank * q + j), lane), s, mapa_u32(barC, lane));
+        }
+        mbar_wait(&bars[2], par);       // the whole r and the partial u's have landed
+        LV_MARK(4);
+        // ---------------------------------------------------------------- D: zp slice = XtX[lo:hi, :] r
+        {
+            double ttw = 0.0;
+            for (int i = warp; i < nsl; i += 2 * nwarp) {
+                const int i2 = i + nwarp;
+                const bool two = i2 < nsl;
+                double z1, z2;
+                if (GS) {
+                    const double2* g1 = reinterpret_cast<const double2*>(g_s + (int64_t)i * pe);
+                    const double2* g2 = reinterpret_cast<const double2*>(g_s + (int64_t)(two ? i2 : i) * pe);
+                    const double2* rr = reinterpret_cast<const double2*>(rfull);
+                    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 4
+                    for (int k2 = lane; k2 < (pe >> 1); k2 += 32) {
+                        const double2 x = rr[k2], u = g1[k2], v = g2[k2];
+                        s0 += u.x * x.x;
+                        s1 += u.y * x.y;
+                        t0 += v.x * x.x;
+                        t1 += v.y * x.y;
+                    }
+                    z1 = warp_sum(s0 + s1);
+                    z2 = warp_sum(t0 + t1);
+                } else {
+                    const double* ra = prm.XtX + (int64_t)(lo + i) * P64;
+                    const double* rb = prm.XtX + (int64_t)(lo + (two ? i2 : i)) * P64;
+                    double s[8], t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s[u] = t[u] = 0.0;
+                    for (int k = lane; k < p; k += 8 * 32) {
+                        double v[8], v2[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool in = k + u * 32 < p;
+                            v[u] = in ? ra[k + u * 32] : 0.0;
+                            v2[u] = in ? rb[k + u * 32] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const double rk = rfull[min(k + u * 32, p - 1)];
+                            s[u] += v[u] * rk;
+                            t[u] += v2[u] * rk;
+                        }
+                    }
+                    z1 = warp_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+                    z2 = warp_sum(((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
+                }
+                ttw += r_s[i] * z1;
+                if (two) ttw += r_s[i2] * z2;
+                if (lane == 0) {
+                    zp_s[i] = z1;
+                    if (two) zp_s[i2] = z2;
+                }
+            }
+            if (lane < ncta) st_async_f64(mapa_u32(smem_u32(exD + rank * 16 + warp), lane), ttw, mapa_u32(barD, lane));
+        }
+        LV_MARK(5);
+        mbar_wait(&bars[3], par);
+        if (tid == 0 && more) {
+            mbar_arrive_expect_tx(&bars[2], bytesC);     // C's phase completed above, D's just now
+            mbar_arrive_expect_tx(&bars[3], bytesD);
+        }
+        LV_MARK(6);
+        // ---------------------------------------------------------------- tt, c, deflate, store
+        double tt;
+        {
+            // 256 per-warp partials, summed in the same order by every warp of every CTA
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += exD[lane * 8 + u];
+            tt = warp_sum(s);
+        }
+        // tt == 0 (r = 0: XtY vanished, more LVs asked than the data carry): the reference divides 0/0;
+        // here the LV is inert (c = 0, P = 0) so predictions stay finite
+        if (tid < q) {
+            double v[ncta];
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) v[cta] = exU[cta * q + tid];
+            double u = 0.0;
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) u += v[cta];
+            const double cv = tt > 0.0 ? u / tt : 0.0;
+            c_s[tid] = cv;
+            if (rank == 0) prm.C[tid + (int64_t)a * q] = cv;
+        }
+        if (rank == 0 && tid == 0) prm.TT[a] = tt;
+        __syncthreads();
+        LV_MARK(7);
+        for (int e = tid; e < nsl * q; e += LV_THREADS) {
+            const int j = e / nsl, i = e - j * nsl;
+            xs[j * sp + i] -= zp_s[i] * c_s[j];
+        }
+        if (tid < nsl) {
+            const double pv = tt > 0.0 ? zp_s[tid] / tt : 0.0;
+            Ps[a * sp + tid] = pv;
+            Rs[a * sp + tid] = r_s[tid];
+            prm.P[lo + tid + (int64_t)a * P64] = pv;
+            prm.R[lo + tid + (int64_t)a * P64] = r_s[tid];
+            prm.W[lo + tid + (int64_t)a * P64] = w_s[tid];
+        }
+        __syncthreads();
+    }
+    cluster.sync();     // no CTA may exit while a peer can still store into its shared memory
+}
+
 #ifdef JCB_K1_TRACE
 static long long* g_lv_trace = nullptr;
 extern "C" int jcb200_debug_lv_trace(long long* host) {
@@ -493,7 +899,7 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
                  int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
                  double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
                  double* dsumw) {
-    // workspace: XtX p*p | XtY p*q | delta p+q | zp 2p | Ppriv, Rpriv LV_CLUSTER*p*nlv each
+    // workspace: XtX p*p | XtY p*q | delta p+q | zp 2p | Ppriv, Rpriv LV_CLUSTER*p*nlv each (8-CTA form only)
     const size_t need = (size_t)(p * p + p * q + (p + q) + 2 * p + 2 * (size_t)LV_CLUSTER * p * nlv) * 8;
     JCB_TRY(ensure(c->solve_ws, need));
     double* XtX = (double*)c->solve_ws.p;
@@ -537,6 +943,49 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
         g_lv_trace = tb;
     }
 #endif
+    // distributed 16-CTA form (q <= 16), with the XtX slice in shared memory when it fits
+    static int lv16_ok = -1;             // -1: not probed; 0: no 16-CTA cluster on this device
+    const bool force8 = getenv("JCB_LV_CLUSTER8") != nullptr;
+    const int per = (int)((p + LV16_CLUSTER - 1) / LV16_CLUSTER);
+    if (q <= 16 && per <= LV_THREADS && nlv <= LV_THREADS && lv16_ok != 0 && !force8) {
+        const size_t max_smem = 227 * 1024 - 64;      // the kernel also holds five mbarriers statically
+        const size_t sm_gs = (size_t)lvd_layout((int)p, (int)q, nlv, per, true).total * 8;
+        const size_t sm_l2 = (size_t)lvd_layout((int)p, (int)q, nlv, per, false).total * 8;
+        const bool gs = sm_gs <= max_smem && getenv("JCB_LV_NO_GS") == nullptr;
+        const size_t smem16 = gs ? sm_gs : sm_l2;
+        if (smem16 <= max_smem) {
+            auto kern = gs ? lvdist_kernel<true> : lvdist_kernel<false>;
+            JCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            JCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(LV16_CLUSTER);
+            cfg.blockDim = dim3(LV_THREADS);
+            cfg.dynamicSmemBytes = smem16;
+            cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = LV16_CLUSTER;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (lv16_ok < 0) {
+                int ncl = 0;
+                const cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+                if (e != cudaSuccess) (void)cudaGetLastError();
+                lv16_ok = (e == cudaSuccess && ncl >= 1) ? 1 : 0;
+            }
+            if (lv16_ok == 1) {
+                prm.xty_smem = 1;
+                phase_begin(c, JCB200_T_LVLOOP);
+                JCB_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+                JCB_LAUNCH_CHECK();
+                phase_end(c, JCB200_T_LVLOOP);
+                return 0;
+            }
+        }
+    }
+    // portable 8-CTA form (any q; XtY in L2 when it does not fit in shared memory)
     size_t smem = (size_t)(3 * p + 4 * q * q + 2 * q + nlv + 64) * 8;
     prm.xty_smem = (smem + (size_t)p * q * 8 <= 160 * 1024) ? 1 : 0;
     if (prm.xty_smem) smem += (size_t)p * q * 8;
