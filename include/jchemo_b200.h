@@ -213,6 +213,14 @@ int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const d
                     const double* dsigma, const double* dM, int64_t ldm, int32_t ncol,
                     const double* dbias, double* dOut, int64_t ldo);
 
+/* K5 on the rows a fit was built from (T = Xc R, plskern.jl:162,170): as jcb200_xmul_dev with M = R, plus the
+ * pivot buffer of the same fit (p + q + 1 doubles, written by jcb200_pivot_dev; may be NULL).  Its last
+ * element is K1's centring decision: when every column has mean^2 <= 64 variance the scores are formed as
+ * X M - mu'M, without a subtraction per element. */
+int jcb200_scores_dev(const double* dX, int64_t ldx, int64_t n, int64_t p, int64_t q, const double* dxmeans,
+                      const double* dxscales, const double* dR, int32_t nlv, const double* d_pivot,
+                      double* dT, int64_t ldt);
+
 /* K6: predictions for every k in k_lo..k_hi in one pass: dPred holds (k_hi-k_lo+1) consecutive
  * m*q matrices (ld = m, stride m*q). */
 int jcb200_predict_sweep_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,

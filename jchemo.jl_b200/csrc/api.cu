@@ -168,6 +168,17 @@ struct Carver {
 
 static inline int64_t even_up(int64_t v) { return (v + 1) & ~(int64_t)1; }
 
+// K5 on the rows the Gram was built from: K1's centring decision (last element of the pivot buffer) lets
+// the score pass skip the per-element centring when every column is well scaled about zero
+static int launch_fit_scores(Ctx* c, const double* dX, int64_t ldx, int64_t n, int64_t p, int64_t q,
+                             const double* dxmeans, const double* dxscales, const double* dR, int nlv,
+                             const double* d_pivot, double* dT, int64_t ldt) {
+    c->xmul_center_flag = d_pivot ? d_pivot + p + q : nullptr;
+    const int r = launch_xmul(c, dX, ldx, n, p, dxmeans, dxscales, dR, p, nlv, nullptr, dT, ldt);
+    c->xmul_center_flag = nullptr;
+    return r;
+}
+
 // the single-GPU fit on device-resident, aligned inputs
 static int fit_dev_locked(Ctx* c, double* dX, int64_t ldx, double* dY, int64_t ldy, const double* dw,
                           int64_t n, int64_t p, int64_t q, int nlv, int scal, int writeback,
@@ -181,8 +192,7 @@ static int fit_dev_locked(Ctx* c, double* dX, int64_t ldx, double* dY, int64_t l
     JCB_TRY(launch_gram(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot, d_packed, 0));
     JCB_TRY(launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans,
                          dxscales, dymeans, dyscales, d_sumw));
-    if (nlv > 0)
-        JCB_TRY(launch_xmul(c, dX, ldx, n, p, dxmeans, dxscales, dR, p, nlv, nullptr, dT, ldt));
+    if (nlv > 0) JCB_TRY(launch_fit_scores(c, dX, ldx, n, p, q, dxmeans, dxscales, dR, nlv, d_pivot, dT, ldt));
     if (dw_out) JCB_TRY(launch_weights(c, dw, n, d_sumw, dw_out));
     if (writeback) {
         phase_begin(c, JCB200_T_WRITEBACK);
@@ -323,7 +333,7 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_TRY(launch_solve(c, s.d_packed, s.d_pivot, p, q, nlv, scal, s.dP, s.dR, s.dW, s.dC, s.dTT, s.dxm,
                              s.dxs, s.dym, s.dys, s.d_sumw));
         if (s.nr > 0) {
-            if (nlv > 0) JCB_TRY(launch_xmul(c, s.dX, s.ld, s.nr, p, s.dxm, s.dxs, s.dR, p, nlv, nullptr, s.dT, s.ld));
+            if (nlv > 0) JCB_TRY(launch_fit_scores(c, s.dX, s.ld, s.nr, p, q, s.dxm, s.dxs, s.dR, nlv, s.d_pivot, s.dT, s.ld));
             JCB_TRY(launch_weights(c, s.dw, s.nr, s.d_sumw, s.dwout));
             if (writeback) {
                 JCB_TRY(launch_center_scale(c, s.dX, s.ld, s.nr, p, s.dxm, s.dxs));
@@ -595,6 +605,15 @@ int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const d
     return launch_xmul(c, dX, ldx, m, p, dmu, dsigma, dM, ldm, ncol, dbias, dOut, ldo);
 }
 
+int jcb200_scores_dev(const double* dX, int64_t ldx, int64_t n, int64_t p, int64_t q, const double* dxmeans,
+                      const double* dxscales, const double* dR, int32_t nlv, const double* d_pivot,
+                      double* dT, int64_t ldt) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dxmeans && dR && dT && n > 0 && p > 0 && q > 0 && nlv >= 0 && ldx >= n && ldt >= n,
+              "scores_dev: bad argument");
+    return launch_fit_scores(c, dX, ldx, n, p, q, dxmeans, dxscales, dR, nlv, d_pivot, dT, ldt);
+}
+
 int jcb200_predict_sweep_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q,
                              const double* dR, const double* dC, int32_t a, const double* dxmeans,
                              const double* dxscales, const double* dymeans, const double* dyscales,
@@ -708,18 +727,29 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     phase_begin(c, JCB200_T_TOTAL);
     // ---- rows are streamed in chunks: the copy of chunk i+1 (copy stream) overlaps K1 on chunk i
     // (compute stream); the partial Grams accumulate in the packed buffer.  The pivot comes from chunk 0.
-    int64_t chunk = n;
+    // Chunks of n/8 rows, the last one cut again into n/16, n/32, n/32: what is left to do on the device when
+    // the last byte has arrived is K1 on 1/32 of the rows instead of 1/8.
+    std::vector<int64_t> bounds;              // chunk ci covers rows [bounds[ci], bounds[ci+1])
+    bounds.push_back(0);
     if (n >= 400000) {
-        chunk = (n + 7) / 8;
+        int64_t chunk = (n + 7) / 8;
         chunk = (chunk + 1) & ~(int64_t)1;              // shards stay 16-byte aligned
+        while (n - bounds.back() > chunk) bounds.push_back(bounds.back() + chunk);
+        const int64_t rest = n - bounds.back();
+        const int64_t half = ((rest / 2) + 1) & ~(int64_t)1, quarter = ((rest / 4) + 1) & ~(int64_t)1;
+        if (quarter >= 4096) {
+            bounds.push_back(bounds.back() + half);
+            bounds.push_back(bounds.back() + quarter);
+        }
     }
-    const int nchunks = (int)((n + chunk - 1) / chunk);
+    bounds.push_back(n);
+    const int nchunks = (int)bounds.size() - 1;
     JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));      // copies must not overtake earlier work on `st`
     JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
     phase_begin_on(c, JCB200_T_H2D, cs);
     if (w) JCB_TRY(h2d_2d(c, dw, ld, w, n, n, 1, cs));
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int64_t r0 = (int64_t)ci * chunk, nr = std::min(chunk, n - r0);
+        const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
         JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
         JCB_TRY(h2d_2d(c, dY + r0, ld, Y + r0, ldy, nr, q, cs));
         if (ci == nchunks - 1) phase_end_on(c, JCB200_T_H2D, cs);
@@ -735,7 +765,25 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     }
     JCB_TRY(launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxm, dxs, dym, dys,
                          d_sumw));
-    if (nlv > 0) JCB_TRY(launch_xmul(c, dX, ld, n, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
+    // Scores: into page-locked T the score pass runs in four row blocks, each block's device-to-host copy
+    // (copy stream) under the next block's K5, so the PCIe transfer of T starts a quarter pass after the solve
+    const bool pipeT = nlv > 0 && n >= 400000 && is_pinned(T);
+    if (pipeT) {
+        int64_t blk = (n + 3) / 4;
+        blk = (blk + 1) & ~(int64_t)1;
+        int bi = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += blk, ++bi) {
+            const int64_t nr = std::min(blk, n - r0);
+            JCB_TRY(launch_fit_scores(c, dX + r0, ld, nr, p, q, dxm, dxs, dR, nlv, d_pivot, dT + r0, ld));
+            JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (bi & 1)], st));
+            JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[1 + (bi & 1)], 0));
+            if (bi == 0) phase_begin_on(c, JCB200_T_D2H, cs);
+            JCB_TRY(d2h_2d(c, T + r0, ldt, dT + r0, ld, nr, nlv, cs));
+        }
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], cs));
+    } else if (nlv > 0) {
+        JCB_TRY(launch_fit_scores(c, dX, ld, n, p, q, dxm, dxs, dR, nlv, d_pivot, dT, ld));
+    }
     JCB_TRY(launch_weights(c, dw, n, d_sumw, dwout));
     if (writeback_xy) {
         phase_begin(c, JCB200_T_WRITEBACK);
@@ -744,7 +792,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
         phase_end(c, JCB200_T_WRITEBACK);
     }
 
-    phase_begin(c, JCB200_T_D2H);
+    if (!pipeT) phase_begin(c, JCB200_T_D2H);
     if (nlv > 0) {
         JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
@@ -756,12 +804,13 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
-    if (nlv > 0) JCB_TRY(d2h_2d(c, T, ldt, dT, ld, n, nlv, st));
+    if (nlv > 0 && !pipeT) JCB_TRY(d2h_2d(c, T, ldt, dT, ld, n, nlv, st));
     JCB_TRY(d2h_2d(c, w_out, n, dwout, ld, n, 1, st));
     if (writeback_xy) {
         JCB_TRY(d2h_2d(c, X, ldx, dX, ld, n, p, st));
         JCB_TRY(d2h_2d(c, Y, ldy, dY, ld, n, q, st));
     }
+    if (pipeT) JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));     // the copies of T on the copy stream
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));

@@ -101,7 +101,7 @@ class Pool {
     bool stop_ = false;
 };
 
-static bool is_pinned(const void* p) {
+bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();

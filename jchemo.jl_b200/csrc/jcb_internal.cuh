@@ -70,6 +70,7 @@ struct Ctx {
     Buf locw_ws;
     Buf solve_ws;
     Buf xmul_ws;
+    const double* xmul_center_flag = nullptr;   // set around the fit's score pass: K1's centring decision (device)
     // general scratch for the host-pointer API
     Buf hX, hY, hW, hT, hSmall, hPred;
     Buf cvX, cvY, cvIdx, cvPk;      // gridcv: permuted copies, row map, per-segment packed buffers
@@ -100,6 +101,7 @@ int h2d_2d(Ctx* c, double* dDst, int64_t ldd, const double* hSrc, int64_t lds, i
 int d2h_2d(Ctx* c, double* hDst, int64_t ldd, const double* dSrc, int64_t lds, int64_t rows, int64_t cols,
            cudaStream_t st);
 void free_staging(Ctx* c);
+bool is_pinned(const void* p);           // page-locked host memory (async copies run at PCIe speed)
 void* pinned_alloc(size_t bytes);
 int pinned_free(void* p);
 void pinned_release_all();

@@ -530,8 +530,8 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     }
 }
 
-// Strided-sample pivot: mean of up to 16384 rows per column, taken as 64 evenly spaced chunks of 256
-// consecutive rows (coalesced 2 KB reads).  One block per column.  The pivot only has to be CLOSE to
+// Strided-sample pivot: mean of up to 16384 rows per column, taken as 16 evenly spaced chunks of 1024
+// consecutive rows (coalesced 2 KB reads; 16 pages per column instead of 64: the kernel is TLB-miss bound).  One block per column.  The pivot only has to be CLOSE to
 // the mean (K3 corrects exactly); a large sample keeps the correction terms c_i s_j and delta delta'
 // far below the rounding level even for offset-heavy data.  ratio[col] = mean^2 / variance of the
 // sample tells how much centring matters for this column.
@@ -552,10 +552,10 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
         }
     } else {
         cnt = 16384;
-        const int64_t stride = n / 64;             // chunk c covers rows [c*stride, c*stride + 256)
+        const int64_t stride = n / 16;             // chunk c covers rows [c*stride, c*stride + 1024)
 #pragma unroll 8
         for (int c = 0; c < 64; ++c) {
-            const double v = src[c * stride + threadIdx.x];
+            const double v = src[(c >> 2) * stride + (c & 3) * 256 + threadIdx.x];
             s += v;
             s2 += v * v;
         }
@@ -587,18 +587,21 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
 // Centring costs FP64-pipe cycles that the DMMAs need.  When every column has mean^2 <= 64 variance,
 // second moments about 0 lose at most ~2 digits to the mean (K3 removes it exactly: pivot = 0 is just
 // another pivot), far inside the 1e-10 budget, so the pivot is zeroed and K1 runs without centring.
-// pivot[p + q] = 1 (centring on) or 0 (pivot all zeros).  JCB_FORCE_CENTER=1 keeps centring on.
+// pivot[p + q] = 1 (the data need centring), 0 (they do not, and the pivot was zeroed: K1 runs without
+// centring; only with JCB_AUTO_NOCENTER=1, because K1 itself gains nothing from it) or 2 (they do not, but
+// K1 keeps its pivot: the default).  K1 centres whenever the flag is non-zero; the score pass K5, where a
+// DADD beside the DMMAs does cost a DMMA slot, goes centre-free on 0 and 2 (k5_xmul.cu).
 __global__ void pivot_decide_kernel(double* __restrict__ pivot, const double* __restrict__ ratio,
                                     int ncol, int force_center) {
     __shared__ int need;
-    if (threadIdx.x == 0) need = force_center;
+    if (threadIdx.x == 0) need = 0;
     __syncthreads();
     for (int c = threadIdx.x; c < ncol; c += blockDim.x)
         if (!(ratio[c] <= 64.0)) need = 1;
     __syncthreads();
-    if (!need)
+    if (!need && !force_center)
         for (int c = threadIdx.x; c < ncol; c += blockDim.x) pivot[c] = 0.0;
-    if (threadIdx.x == 0) pivot[ncol] = need ? 1.0 : 0.0;
+    if (threadIdx.x == 0) pivot[ncol] = need ? 1.0 : (force_center ? 2.0 : 0.0);
 }
 
 // ------------------------------------------------------------------------------------------ host

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "jcb_internal.cuh"
 
@@ -48,6 +49,8 @@ struct XmulParams {
     int64_t ldo;
     int ncol;              // real output columns in this pass
     int aligned;           // X is 16-byte aligned with even ldx: bulk copies allowed
+    const double* cflag;   // device flag of the fit (pivot[p+q]): != 1.0 = every column has mean^2 <= 64 var, so the
+                           // scores may be formed as X M - mu'M (no DADD per element beside the DMMAs); else null
     // sweep epilogue
     const double* Cy;      // [a][q]: C[j,k] * yscales[j]
     const double* ymeans;
@@ -104,7 +107,8 @@ xmul_kernel(const XmulParams prm) {
     double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NPT][132]
     double* mu_s = out_s + NPT * XM_PITCH;                                        // nchunk*32
     double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
-    uint64_t* full = reinterpret_cast<uint64_t*>(cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0));
+    double* cb_s = cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0);          // NPT (+ pad): -mu'M, centre-free path
+    uint64_t* full = reinterpret_cast<uint64_t*>(cb_s + 64 + 8);
     uint64_t* empty = full + nstage;
     uint64_t* tfull = empty + nstage;      // sweep: score tile in out_s complete (consumers -> epilogue warps)
     uint64_t* tempty = tfull + 1;          // sweep: out_s read out (epilogue warps -> consumers)
@@ -113,6 +117,22 @@ xmul_kernel(const XmulParams prm) {
     for (int k = threadIdx.x; k < prm.nchunk * XM_KC; k += XM_THREADS) mu_s[k] = prm.mu[k];
     if (SWEEP)
         for (int k = threadIdx.x; k < prm.ncol * prm.q; k += XM_THREADS) cy_s[k] = prm.Cy[k];
+    // Centring costs two DADDs per k4-step beside six DMMAs, and on sm_100a a DADD issued into a DMMA stream
+    // takes about a DMMA slot of the shared FP64 pipe.  When the fit's pivot pass found every column well
+    // scaled about zero (mean^2 <= 64 var: at most two digits to lose), T = X M - mu'M: raw fragments into
+    // the DMMAs and one constant per output column in the epilogue.
+    const bool center = SWEEP || !(prm.cflag != nullptr && *prm.cflag != 1.0);
+    if (!SWEEP && !center) {
+        __syncthreads();                                   // mu_s complete
+        for (int col = warp; col < NPT; col += XM_THREADS / 32) {
+            double sacc = 0.0;
+            for (int k = lane; k < prm.nchunk * XM_KC; k += 32)
+                sacc += mu_s[k] * prm.Mt[((int64_t)(k / XM_KC) * NPT + col) * XM_MPITCH + (k % XM_KC)];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane == 0) cb_s[col] = -sacc;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
@@ -232,36 +252,43 @@ xmul_kernel(const XmulParams prm) {
 #pragma unroll
             for (int e = 0; e < NEX; ++e) ex[h][e] = 0.0;
         }
-        for (int ch = 0; ch < nchunk; ++ch, ++it) {
-            const int buf = it % nstage;
-            const uint32_t ph = (it / nstage) & 1;
-            mbar_wait(&full[buf], ph);
-            const double* xs = reinterpret_cast<const double*>(stage_base + (size_t)buf * STAGE);
-            const double* ms = xs + XM_KC * XM_PITCH;
-            const double* mus = mu_s + ch * XM_KC;
+        auto chunk_loop = [&](auto cen_tag) {
+            constexpr bool CEN = decltype(cen_tag)::value;
+            for (int ch = 0; ch < nchunk; ++ch, ++it) {
+                const int buf = it % nstage;
+                const uint32_t ph = (it / nstage) & 1;
+                mbar_wait(&full[buf], ph);
+                const double* xs = reinterpret_cast<const double*>(stage_base + (size_t)buf * STAGE);
+                const double* ms = xs + XM_KC * XM_PITCH;
+                const double* mus = mu_s + ch * XM_KC;
 #pragma unroll
-            for (int k4 = 0; k4 < XM_KC / 4; ++k4) {
-                const int k = k4 * 4 + kk;
-                double2 a = *reinterpret_cast<const double2*>(xs + k * XM_PITCH + m0 + 2 * g);
-                const double mk = mus[k];
-                a.x -= mk;
-                a.y -= mk;
+                for (int k4 = 0; k4 < XM_KC / 4; ++k4) {
+                    const int k = k4 * 4 + kk;
+                    double2 a = *reinterpret_cast<const double2*>(xs + k * XM_PITCH + m0 + 2 * g);
+                    if (CEN) {
+                        const double mk = mus[k];
+                        a.x -= mk;
+                        a.y -= mk;
+                    }
 #pragma unroll
-                for (int nb = 0; nb < NPB; ++nb) {
-                    const double b = ms[(nb * 8 + g) * XM_MPITCH + k];
-                    dmma(acc[0][nb][0], acc[0][nb][1], a.x, b);
-                    dmma(acc[1][nb][0], acc[1][nb][1], a.y, b);
+                    for (int nb = 0; nb < NPB; ++nb) {
+                        const double b = ms[(nb * 8 + g) * XM_MPITCH + k];
+                        dmma(acc[0][nb][0], acc[0][nb][1], a.x, b);
+                        dmma(acc[1][nb][0], acc[1][nb][1], a.y, b);
+                    }
+#pragma unroll
+                    for (int e = 0; e < NEX; ++e) {
+                        const double b = ms[(NP + e) * XM_MPITCH + k];
+                        ex[0][e] += a.x * b;
+                        ex[1][e] += a.y * b;
+                    }
                 }
-#pragma unroll
-                for (int e = 0; e < NEX; ++e) {
-                    const double b = ms[(NP + e) * XM_MPITCH + k];
-                    ex[0][e] += a.x * b;
-                    ex[1][e] += a.y * b;
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);
-        }
+        };
+        if (center) chunk_loop(std::true_type{});
+        else chunk_loop(std::false_type{});
         // ---- epilogue: fragments -> shared (this warp's 16 rows) -> 128-byte global rows
         if (SWEEP && tn > 0) mbar_wait(tempty, (tn - 1) & 1);     // the previous tile has been read out
 #pragma unroll
@@ -287,6 +314,7 @@ xmul_kernel(const XmulParams prm) {
             for (int col = half; col < prm.ncol; col += 2) {
                 if (rok) {
                     double v = out_s[col * XM_PITCH + m0 + r];
+                    if (!center) v += cb_s[col];
                     if (prm.bias) v += prm.bias[col];
                     prm.Out[row0 + m0 + r + (int64_t)col * prm.ldo] = v;
                 }
@@ -315,7 +343,7 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     constexpr int XM_PITCH = XM_MT + 4;
     constexpr int XM_THREADS = (NCW + 1 + xm_epw<SWEEP, NCW>()) * 32;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
-    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 +
+    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 + (64 + 8) * 8 +
                       (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
     int nstage = (int)(((XM_OCC == 2 ? 110 : 220) * 1024 - fixed) / stage);
     if (nstage > 4) nstage = 4;
@@ -422,6 +450,7 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
         prm.ldo = ldo;
         prm.ncol = ncol;
         prm.aligned = aligned;
+        prm.cflag = sweep ? nullptr : c->xmul_center_flag;
         if (sweep) {
             sweep_cy_kernel<<<(ncol * q + 255) / 256, 256, 0, c->stream>>>(dC, dys, q, ncol, Cy);
             JCB_LAUNCH_CHECK();

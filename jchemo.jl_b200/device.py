@@ -100,9 +100,15 @@ def solve_dev(packed, pivot, model, scal=False):
         _p(model.yscales), _p(model.sumw)), "solve_dev")
 
 
-def scores_dev(X, n, model, out=None):
-    """T = ((X - xmeans) ./ xscales) * R for the rows of X (fit scores or transform)."""
+def scores_dev(X, n, model, out=None, pivot=None):
+    """T = ((X - xmeans) ./ xscales) * R for the rows of X (fit scores or transform).  `pivot`: the pivot
+    buffer of the fit these rows belong to (carries K1's centring decision), fit scores only."""
     out = model.T if out is None else out
+    if pivot is not None:
+        _lib.check(_lib.lib().jcb200_scores_dev(_p(X), X.shape[1], n, model.p, model.q, _p(model.xmeans),
+                                                _p(model.xscales), _p(model.R), model.nlv, _p(pivot),
+                                                _p(out), out.shape[1]), "scores_dev")
+        return out
     _lib.check(_lib.lib().jcb200_xmul_dev(_p(X), X.shape[1], n, model.p, _p(model.xmeans),
                                           _p(model.xscales), _p(model.R), model.p, model.nlv, None,
                                           _p(out), out.shape[1]), "xmul_dev")

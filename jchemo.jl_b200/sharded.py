@@ -50,6 +50,6 @@ def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, pac
     reduce_packed(packed, group)
     dev.solve_dev(packed, pivot, model, scal)
     if model.nlv > 0:
-        dev.scores_dev(X, n_local, model)
+        dev.scores_dev(X, n_local, model, pivot=pivot)
     dev.weights_dev(w, n_local, model)
     return model

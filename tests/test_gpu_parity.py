@@ -428,3 +428,36 @@ def test_locwlv_neighbourhood_sizes(jc):
         ref = oracle.locwlv(Xtr, Ytr, X, listnn=listnn, nlv=range(0, nlv + 1))
         for a in range(nlv + 1):
             assert relerr(got[a], ref[a]) < 1e-11, (k, a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,q,nlv,scal", [
+    (300, 5, 2, 5, False),       # p < 16: most CTAs of the cluster own an empty slice
+    (400, 17, 16, 10, True),     # widest warp-level eigenproblem, odd p
+    (400, 33, 17, 8, False),     # q > 16: portable 8-CTA form with the generic eigen path
+    (3000, 700, 3, 40, True),    # XtX slice too large for shared memory: rows from L2
+    (2500, 610, 1, 12, False),   # q = 1, shared-memory slice at its size limit
+    (1500, 100, 4, 90, False),   # nlv > 64: several rounds of the dot exchange
+])
+def test_lvloop_forms(jc, n, p, q, nlv, scal):
+    """Every form of the LV-loop kernel (distributed 16-CTA cluster with the XtX slice in shared memory or
+    in L2; portable 8-CTA fallback) against the oracle, on data with a real X-Y relation so that every
+    requested LV is well determined."""
+    rng = np.random.default_rng(7)
+    X = synth.synth_matrix(1, n, p)
+    B = rng.standard_normal((p, q))
+    Y = X @ B + 0.1 * synth.synth_matrix(2, n, q)
+    fm = jc.plskern(X, Y, nlv=nlv, scal=scal)
+    ref = oracle.plskern(X, Y, nlv=nlv, scal=scal)
+    k = min(nlv, p)
+    assert fm.T.shape == (n, k)
+    # LVs far beyond the signal's rank are rounding noise in the reference too: grade the leading ones
+    lead = min(k, max(q, 6))
+    s = oracle.sign_align(ref, fm)
+    assert relerr((fm.T * s)[:, :lead], ref.T[:, :lead]) < TOL
+    assert relerr((fm.W * s)[:, :lead], ref.W[:, :lead]) < TOL
+    assert relerr(fm.TT[:lead], ref.TT[:lead]) < TOL
+    assert relerr(jc.coef(fm, nlv=lead).B, oracle.coef(ref, nlv=lead)[0]) < TOL
+    assert relerr(jc.predict(fm, X[:64]).pred, oracle.predict(ref, X[:64])) < TOL
+    np.testing.assert_allclose(np.linalg.norm(fm.W, axis=0), 1, atol=1e-12)
+    assert np.abs(fm.P[:, :lead].T @ fm.R[:, :lead] - np.eye(lead)).max() < TOL
