@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -108,6 +109,8 @@ static int init_ctx(Ctx* c, int device) {
     c->num_sms = prop.multiProcessorCount;
     JCB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     JCB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    JCB_CUDA(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->pipe_ev[i], cudaEventDisableTiming));
     c->stream = c->own_stream;
     for (int i = 0; i < JCB200_NPHASE; ++i) {
         JCB_CUDA(cudaEventCreate(&c->ev_begin[i]));
@@ -497,6 +500,8 @@ static void destroy_ctx(Ctx* c) {
     }
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->out_stream);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->pipe_ev[i]);
     c->ready = false;
 }
 
@@ -818,6 +823,90 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     return 0;
 }
 
+// Row-chunk pipeline of the streaming host paths (transform, predict): new rows are independent, so the
+// host-to-device copy of chunk i+1 (copy stream), the kernel on chunk i (compute stream) and the
+// device-to-host copy of the results of chunk i-1 (out stream) run at the same time — PCIe is full duplex,
+// and a sweep that returns as many bytes as it reads (C5: 4 GB in, 4 GB out) takes the time of one direction.
+// compute(ci, r0, nr, slot) runs on c->stream, copy_out(ci, r0, nr, slot, stream) on the out stream; results
+// that live in a per-chunk buffer use `slot` = ci & 1, which is not reused before its copy-out has finished.
+extern "C++" {
+template <class Compute, class CopyOut>
+static int pipeline_rows(Ctx* c, const double* X, int64_t ldx, int64_t m, int64_t p, double* dX, int64_t ld,
+                         int64_t chunk, Compute compute, CopyOut copy_out) {
+    cudaStream_t st = c->stream, cs = c->copy_stream, os = c->out_stream;
+    // JCB_PIPE_TRACE=1: per-chunk completion times of the three legs on stderr (debugging aid)
+    static const bool trace = getenv("JCB_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<const char*> tname;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+        tname.push_back(s == c->copy_stream ? "h2d" : (s == c->out_stream ? "d2h" : "compute"));
+        fprintf(stderr, "host: mark %zu (%s) enqueued at %.2f ms\n", tev.size() - 1, tname.back(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+    };
+    mark(st);
+    JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));      // neither leg may overtake earlier work on `st`
+    JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
+    JCB_CUDA(cudaStreamWaitEvent(os, c->chunk_ev[0], 0));
+    phase_begin_on(c, JCB200_T_H2D, cs);
+    const int nch = (int)((m + chunk - 1) / chunk);
+    // The host paces the pipeline so that NO copy is queued ahead of a kernel: the kernel on chunk i is enqueued
+    // once its rows have landed, and only then the copy of chunk i+1, then the copy-out of chunk i.  Measured on
+    // B200 (bench/pipe_trace.py, JCB_PIPE_TRACE=1): with copies queued ahead, work enqueued later on the compute
+    // stream was not started before those copies had finished — two chunks late with one hardware work queue
+    // (CUDA_DEVICE_MAX_CONNECTIONS=1), and on most calls only after the LAST copy with the default eight.  The
+    // call is synchronous anyway; the host wait costs the copy engine a few tens of microseconds per chunk.
+    auto issue_h2d = [&](int ci) -> int {
+        const int64_t r0 = (int64_t)ci * chunk, nr = std::min(chunk, m - r0);
+        JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
+        mark(cs);
+        if (ci == nch - 1) phase_end_on(c, JCB200_T_H2D, cs);
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
+        return 0;
+    };
+    JCB_TRY(issue_h2d(0));
+    int ci = 0;
+    for (; ci < nch; ++ci) {
+        const int64_t r0 = (int64_t)ci * chunk, nr = std::min(chunk, m - r0);
+        const int slot = ci & 1;
+        JCB_CUDA(cudaEventSynchronize(c->chunk_ev[1 + slot]));
+        if (ci >= 2) JCB_CUDA(cudaStreamWaitEvent(st, c->pipe_ev[2 + slot], 0));
+        mark(st);
+        JCB_TRY(compute(ci, r0, nr, slot));
+        mark(st);
+        JCB_CUDA(cudaEventRecord(c->pipe_ev[slot], st));
+        if (ci + 1 < nch) JCB_TRY(issue_h2d(ci + 1));
+        JCB_CUDA(cudaStreamWaitEvent(os, c->pipe_ev[slot], 0));
+        if (ci == 0) phase_begin_on(c, JCB200_T_D2H, os);
+        JCB_TRY(copy_out(ci, r0, nr, slot, os));
+        mark(os);
+        JCB_CUDA(cudaEventRecord(c->pipe_ev[2 + slot], os));
+    }
+    JCB_CUDA(cudaStreamWaitEvent(st, c->pipe_ev[2], 0));
+    if (ci > 1) JCB_CUDA(cudaStreamWaitEvent(st, c->pipe_ev[3], 0));
+    phase_end(c, JCB200_T_D2H);
+    if (trace) {
+        cudaStreamSynchronize(st);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            fprintf(stderr, "pipe mark %zu (%s) done at %.2f ms\n", i, tname[i], ms);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    return 0;
+}
+static int64_t pipeline_chunk(int64_t m) {
+    if (m < 400000) return even_up(m);
+    return even_up((m + 7) / 8);
+}
+}  // extern "C++"
+
 int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const double* xmeans,
                      const double* xscales, const double* R, int32_t nlv, double* T_out,
                      int64_t ldt) {
@@ -839,16 +928,17 @@ int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const d
     cudaStream_t st = c->stream;
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
-    phase_begin(c, JCB200_T_H2D);
-    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
     JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
-    phase_end(c, JCB200_T_H2D);
-    JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
-    phase_begin(c, JCB200_T_D2H);
-    JCB_TRY(d2h_2d(c, T_out, ldt, dT, ld, m, nlv, st));
-    phase_end(c, JCB200_T_D2H);
+    JCB_TRY(pipeline_rows(
+        c, X, ldx, m, p, dX, ld, pipeline_chunk(m),
+        [&](int, int64_t r0, int64_t nr, int) {
+            return launch_xmul(c, dX + r0, ld, nr, p, dxm, dxs, dR, p, nlv, nullptr, dT + r0, ld);
+        },
+        [&](int, int64_t r0, int64_t nr, int, cudaStream_t os) {
+            return d2h_2d(c, T_out + r0, ldt, dT + r0, ld, nr, nlv, os);
+        }));
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);
@@ -864,10 +954,13 @@ int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double
     const int64_t ld = even_up(m);
     JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
     JCB_TRY(ensure(c->hT, (size_t)ld * std::max<int>(nlv, 1) * 8));
+    const int64_t chunk = pipeline_chunk(m), cmax = even_up(std::min(chunk, m));
+    JCB_TRY(ensure(c->hPred, (size_t)2 * cmax * p * 8));           // two chunk-local result slots (ld = cmax)
     JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + 2 * (size_t)p * nlv + 16) * 8));
     c->cv_hostX = c->cv_hostY = nullptr;
     double* dX = (double*)c->hX.p;
     double* dT = (double*)c->hT.p;
+    double* dOut = (double*)c->hPred.p;
     Carver cv(c->hSmall.p);
     double* dxm = cv.take(p);
     double* dxs = cv.take(p);
@@ -876,22 +969,23 @@ int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double
     cudaStream_t st = c->stream;
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
-    phase_begin(c, JCB200_T_H2D);
-    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
     JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     if (nlv > 0) {
         JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
         JCB_CUDA(cudaMemcpyAsync(dP, P, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
     }
-    phase_end(c, JCB200_T_H2D);
-    phase_begin(c, JCB200_T_SCORES);
-    if (nlv > 0) JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, nlv, nullptr, dT, ld));
-    JCB_TRY(launch_xfit(c, dX, ld, m, p, dT, ld, dP, p, nlv, dxm, dxs, resid));
-    phase_end(c, JCB200_T_SCORES);
-    phase_begin(c, JCB200_T_D2H);
-    JCB_TRY(d2h_2d(c, out, ldo, dX, ld, m, p, st));
-    phase_end(c, JCB200_T_D2H);
+    // m x p in and m x p out: the two directions of the link overlap chunk by chunk
+    JCB_TRY(pipeline_rows(
+        c, X, ldx, m, p, dX, ld, chunk,
+        [&](int, int64_t r0, int64_t nr, int slot) {
+            if (nlv > 0) JCB_TRY(launch_xmul(c, dX + r0, ld, nr, p, dxm, dxs, dR, p, nlv, nullptr, dT + r0, ld));
+            return launch_xfit(c, dX + r0, ld, dOut + (size_t)slot * cmax * p, cmax, nr, p, dT + r0, ld, dP, p,
+                               nlv, dxm, dxs, resid);
+        },
+        [&](int, int64_t r0, int64_t nr, int slot, cudaStream_t os) {
+            return d2h_2d(c, out + r0, ldo, dOut + (size_t)slot * cmax * p, cmax, nr, p, os);
+        }));
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);
@@ -944,8 +1038,10 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     const int nk = k_hi - k_lo + 1;
     for (int i = 0; i < nk; ++i) ARG_CHECK(pred_out[i], "predict_sweep: NULL output matrix");
     const int64_t ld = even_up(m);
+    const int64_t chunk = pipeline_chunk(m);
+    const int64_t cmax = std::min(chunk, m);             // rows of the largest chunk
     JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    JCB_TRY(ensure(c->hPred, (size_t)nk * m * q * 8));
+    JCB_TRY(ensure(c->hPred, (size_t)2 * nk * cmax * q * 8));      // two chunk-local result slots
     const size_t nd = (size_t)p * a + (size_t)q * a + 2 * (p + q) + (size_t)p * q + q + 64;
     JCB_TRY(ensure(c->hSmall, nd * 8));
     double* dX = (double*)c->hX.p;
@@ -962,8 +1058,6 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     cudaStream_t st = c->stream;
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
-    phase_begin(c, JCB200_T_H2D);
-    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
     if (a > 0) {
         JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * a * 8, cudaMemcpyHostToDevice, st));
         JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * a * 8, cudaMemcpyHostToDevice, st));
@@ -972,19 +1066,23 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dym, ymeans, q * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dys, yscales, q * 8, cudaMemcpyHostToDevice, st));
-    phase_end(c, JCB200_T_H2D);
-    if (nk == 1 && k_lo > 0) {
-        // single k: the reference's own arithmetic, pred = int + X B (plskern.jl:233-234),
-        // as ymeans + (X - xmeans) B
-        JCB_TRY(launch_coef(c, dR, dC, dxm, dxs, dym, dys, p, q, k_lo, dB, dint));
-        JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, nullptr, dB, p, (int)q, dym, dPred, m));
-    } else {
-        JCB_TRY(launch_predict_sweep(c, dX, ld, m, p, q, dR, dC, a, dxm, dxs, dym, dys, k_lo, k_hi,
-                                     dPred));
-    }
-    phase_begin(c, JCB200_T_D2H);
-    for (int i = 0; i < nk; ++i) JCB_TRY(d2h_2d(c, pred_out[i], m, dPred + (size_t)i * m * q, m, m, q, st));
-    phase_end(c, JCB200_T_D2H);
+    const bool single = nk == 1 && k_lo > 0;
+    // single k: the reference's own arithmetic, pred = int + X B (plskern.jl:233-234), as ymeans + (X - xmeans) B
+    if (single) JCB_TRY(launch_coef(c, dR, dC, dxm, dxs, dym, dys, p, q, k_lo, dB, dint));
+    // the results of a chunk are nk chunk-local nr x q matrices (ld = nr) in its slot of dPred
+    JCB_TRY(pipeline_rows(
+        c, X, ldx, m, p, dX, ld, chunk,
+        [&](int, int64_t r0, int64_t nr, int slot) {
+            double* dP = dPred + (size_t)slot * nk * cmax * q;
+            if (single) return launch_xmul(c, dX + r0, ld, nr, p, dxm, nullptr, dB, p, (int)q, dym, dP, nr);
+            return launch_predict_sweep(c, dX + r0, ld, nr, p, q, dR, dC, a, dxm, dxs, dym, dys, k_lo, k_hi, dP);
+        },
+        [&](int, int64_t r0, int64_t nr, int slot, cudaStream_t os) {
+            const double* dP = dPred + (size_t)slot * nk * cmax * q;
+            for (int i = 0; i < nk; ++i)
+                JCB_TRY(d2h_2d(c, pred_out[i] + r0, m, dP + (size_t)i * nr * q, nr, nr, q, os));
+            return 0;
+        }));
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);

@@ -222,7 +222,7 @@ struct PinnedBlock {
 };
 static std::mutex g_pool_mutex;
 static std::vector<PinnedBlock> g_pool;
-constexpr size_t POOL_KEEP_BYTES = (size_t)3 << 30;
+constexpr size_t POOL_KEEP_BYTES = (size_t)6 << 30;     // a C5 predict sweep returns 4.1 GB
 
 void* pinned_alloc(size_t bytes) {
     std::lock_guard<std::mutex> lk(g_pool_mutex);

@@ -52,6 +52,8 @@ struct Ctx {
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t out_stream = nullptr;   // device-to-host leg of the row-chunk pipelines (transform, predict)
+    cudaEvent_t pipe_ev[4];              // [0..1] chunk computed, [2..3] chunk copied out
     cudaStream_t stream = nullptr;   // stream in use (own_stream or external)
     // K1 scratch
     Buf partials;        // split-K partial units
@@ -134,8 +136,9 @@ int launch_sstot(Ctx* c, const double* dX, int64_t ldx, int64_t n, int64_t p, co
 int launch_locw(Ctx* c, const double* dXtr, int64_t ldxt, const double* dYtr, int64_t ldyt, int64_t ntr,
                 const double* dX, int64_t ldx, int64_t m, int64_t p, int64_t q, const int64_t* d_idx,
                 const int64_t* d_off, const double* d_w, int kmax, int k_lo, int k_hi, int scal, double* d_pred);
-int launch_xfit(Ctx* c, double* dX, int64_t ldx, int64_t m, int64_t p, const double* dT, int64_t ldt,
-                const double* dP, int64_t ldp, int nlv, const double* dxm, const double* dxs, int resid);
+int launch_xfit(Ctx* c, const double* dX, int64_t ldx, double* dOut, int64_t ldo, int64_t m, int64_t p,
+                const double* dT, int64_t ldt, const double* dP, int64_t ldp, int nlv, const double* dxm,
+                const double* dxs, int resid);
 int launch_coef(Ctx* c, const double* dR, const double* dC, const double* dxmeans,
                 const double* dxscales, const double* dymeans, const double* dyscales, int64_t p,
                 int64_t q, int k, double* dB, double* dint);

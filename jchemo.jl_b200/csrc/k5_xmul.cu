@@ -62,7 +62,11 @@ struct XmulParams {
 // packs M (p x ncol, ld ldm) into Mt[chunk][n][36] with 1/sigma folded in; pads mu
 __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, const double* __restrict__ sigma,
                                  const double* __restrict__ mu, int p, int ncol, int NP, int nchunk,
-                                 double* __restrict__ Mt, double* __restrict__ mu_pad) {
+                                 double* __restrict__ Mt, double* __restrict__ mu_pad, double* __restrict__ zeros) {
+    // the 128 zero doubles that stand in for padding columns: written here, by a kernel — a cudaMemsetAsync may
+    // be scheduled on the copy engine that is busy with the host-to-device stream of the row-chunk pipelines,
+    // and would hold the compute stream back until the whole transfer has finished
+    if (blockIdx.x == 0 && threadIdx.x < 128) zeros[threadIdx.x] = 0.0;
     const int64_t total = (int64_t)nchunk * NP * XM_MPITCH;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
@@ -420,7 +424,6 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
     double* bias_pad = mu_pad + (size_t)nchunk * XM_KC;
     double* Cy = bias_pad + 64;
     double* Mt = Cy + (size_t)maxcol * (q > 0 ? q : 1);
-    JCB_CUDA(cudaMemsetAsync(zeros, 0, 128 * 8, c->stream));
     const int aligned = (((uintptr_t)dX & 15) == 0 && (ldx & 1) == 0) ? 1 : 0;
 
     for (int c0 = 0; c0 < ncol_total; c0 += maxcol) {
@@ -433,7 +436,7 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
         }
         const int NP = npb * 8 + nex;
         xmul_pack_kernel<<<64, 256, 0, c->stream>>>(dM + (int64_t)c0 * ldm, ldm, dsigma, dmu, (int)p, ncol,
-                                                    NP, nchunk, Mt, mu_pad);
+                                                    NP, nchunk, Mt, mu_pad, zeros);
         JCB_LAUNCH_CHECK();
         XmulParams prm;
         memset(&prm, 0, sizeof(prm));

@@ -181,7 +181,7 @@ def _bang_mat(X, name):
 def xfit(obj, X, *, nlv=None):
     """xfit(object::Plsr, X; nlv = nothing), `/root/reference/src/xfit.jl:33-35`: X_fit in the original scale."""
     X = _fmat(X)
-    return _xfit(obj, X, nlv, 0, np.empty(X.shape, order="F"))
+    return _xfit(obj, X, nlv, 0, _out_empty(X.shape))
 
 
 def xfit_bang(obj, X, *, nlv=None):
@@ -193,7 +193,7 @@ def xfit_bang(obj, X, *, nlv=None):
 def xresid(obj, X, *, nlv=None):
     """xresid(object, X; nlv = nothing) (xfit.jl:88-90): E = X - X_fit."""
     X = _fmat(X)
-    return _xfit(obj, X, nlv, 1, np.empty(X.shape, order="F"))
+    return _xfit(obj, X, nlv, 1, _out_empty(X.shape))
 
 
 def xresid_bang(obj, X, *, nlv=None):
@@ -236,7 +236,7 @@ def predict(obj, X, *, nlv=None):
     nk = k_hi - k_lo + 1
     if nk <= 0:
         return PredResult([])
-    preds = [np.empty((m, q), order="F") for _ in range(nk)]
+    preds = [_out_empty((m, q)) for _ in range(nk)]
     if m > 0:
         arr = (C.c_void_p * nk)(*[pm.ctypes.data for pm in preds])
         R, Cm = np.asfortranarray(obj.R), np.asfortranarray(obj.C)
