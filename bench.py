@@ -289,10 +289,9 @@ def main():
                   model.ymeans, model.yscales, model.weights)]
 
         def e2e_step():
-            X[:, :n_loc].copy_(hX, non_blocking=True)
-            Y[:, :n_loc].copy_(hY, non_blocking=True)
-            step()
-            hT.copy_(model.T[:NLV, :n_loc], non_blocking=True)
+            # this rank's rows streamed from page-locked host memory under K1, scores copied back under K5
+            sharded.fit_sharded_from_host(hX, hY, None, X, Y, None, n_loc, model, scal=False, pivot=pivot,
+                                          packed=packed, hT=hT)
             for h, d in zip(small, (model.P, model.R, model.W, model.C, model.TT, model.xmeans,
                                     model.xscales, model.ymeans, model.yscales, model.weights)):
                 h.copy_(d, non_blocking=True)
@@ -308,7 +307,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item()) / Ke * 1e-3
         e2e_phases = None
-        e2e_how = "per rank: pinned host -> device copies + sharded fit + device -> host of T and model"
+        e2e_how = ("per rank: sharded.fit_sharded_from_host (row chunks from pinned host memory under K1, one packed-Gram "
+                   "all-reduce, scores copied back in row blocks under K5) + device -> host of the model")
     e2e_val = f_fit(n_glob, P, Q, NLV) / e2e_s * 1e-12
 
     if rank != 0:

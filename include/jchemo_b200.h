@@ -213,6 +213,12 @@ int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const d
                     const double* dsigma, const double* dM, int64_t ldm, int32_t ncol,
                     const double* dbias, double* dOut, int64_t ldo);
 
+/* Plumbing for the streamed sharded fit: asynchronous copy of a rows x cols block of a column-major matrix
+ * between page-locked host memory and the device (one strided DMA, cudaMemcpy2DAsync) on the caller's stream;
+ * to_device = 1 host -> device, 0 device -> host. */
+int jcb200_copy_rows_async(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
+                           int32_t to_device, void* cuda_stream);
+
 /* K5 on the rows a fit was built from (T = Xc R, plskern.jl:162,170): as jcb200_xmul_dev with M = R, plus the
  * pivot buffer of the same fit (p + q + 1 doubles, written by jcb200_pivot_dev; may be NULL).  Its last
  * element is K1's centring decision: when every column has mean^2 <= 64 variance the scores are formed as

@@ -53,6 +53,7 @@ SIGNATURES = {
     "jcb200_solve_dev": (C.c_int, [C.c_void_p, C.c_void_p, i64, i64, i32, i32] + [C.c_void_p] * 10),
     "jcb200_xmul_dev": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i64,
                                   i32, C.c_void_p, C.c_void_p, i64]),
+    "jcb200_copy_rows_async": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32, C.c_void_p]),
     "jcb200_scores_dev": (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i32,
                                     C.c_void_p, C.c_void_p, i64]),
     "jcb200_predict_sweep_dev": (C.c_int, [C.c_void_p, i64, i64, i64, i64, C.c_void_p, C.c_void_p, i32] +

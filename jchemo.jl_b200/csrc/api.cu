@@ -610,6 +610,17 @@ int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const d
     return launch_xmul(c, dX, ldx, m, p, dmu, dsigma, dM, ldm, ncol, dbias, dOut, ldo);
 }
 
+int jcb200_copy_rows_async(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols,
+                           int32_t to_device, void* cuda_stream) {
+    API_PROLOGUE();
+    ARG_CHECK(dst && src && rows >= 0 && cols >= 0 && ldd >= rows && lds >= rows, "copy_rows_async: bad argument");
+    if (rows == 0 || cols == 0) return 0;
+    JCB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols,
+                               to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                               (cudaStream_t)cuda_stream));
+    return 0;
+}
+
 int jcb200_scores_dev(const double* dX, int64_t ldx, int64_t n, int64_t p, int64_t q, const double* dxmeans,
                       const double* dxscales, const double* dR, int32_t nlv, const double* d_pivot,
                       double* dT, int64_t ldt) {

@@ -82,13 +82,28 @@ def packed_len(p, q):
     return int(_lib.lib().jcb200_packed_len(p, q))
 
 
+def _ld(t):
+    """Leading dimension of a [cols, ld] tensor or of a row-block view t[:, r0:r1] of one."""
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def copy_rows_async(dst, src, rows, stream):
+    """dst[:, :rows] <- src[:, :rows] between a page-locked host tensor and a device tensor (either direction;
+    both [cols, ld] or row-block views): one strided DMA on `stream` (torch's own copy_ of a strided view
+    goes through a contiguous temporary on the host)."""
+    to_device = 1 if dst.is_cuda else 0
+    _lib.check(_lib.lib().jcb200_copy_rows_async(_p(dst), _ld(dst), _p(src), _ld(src), rows, dst.shape[0],
+                                                 to_device, C.c_void_p(stream.cuda_stream)), "copy_rows_async")
+
+
 def pivot_dev(X, Y, n, pivot):
-    _lib.check(_lib.lib().jcb200_pivot_dev(_p(X), X.shape[1], _p(Y), Y.shape[1], n, X.shape[0],
+    _lib.check(_lib.lib().jcb200_pivot_dev(_p(X), _ld(X), _p(Y), _ld(Y), n, X.shape[0],
                                            Y.shape[0], _p(pivot)), "pivot_dev")
 
 
 def gram_dev(X, Y, w, n, pivot, packed, accumulate=False):
-    _lib.check(_lib.lib().jcb200_gram_dev(_p(X), X.shape[1], _p(Y), Y.shape[1], _p(w), n, X.shape[0],
+    """Partial Gram of n rows (X, Y may be row-block views); accumulate=True adds to `packed`."""
+    _lib.check(_lib.lib().jcb200_gram_dev(_p(X), _ld(X), _p(Y), _ld(Y), _p(w), n, X.shape[0],
                                           Y.shape[0], _p(pivot), _p(packed), int(accumulate)),
                "gram_dev")
 
@@ -105,9 +120,9 @@ def scores_dev(X, n, model, out=None, pivot=None):
     buffer of the fit these rows belong to (carries K1's centring decision), fit scores only."""
     out = model.T if out is None else out
     if pivot is not None:
-        _lib.check(_lib.lib().jcb200_scores_dev(_p(X), X.shape[1], n, model.p, model.q, _p(model.xmeans),
+        _lib.check(_lib.lib().jcb200_scores_dev(_p(X), _ld(X), n, model.p, model.q, _p(model.xmeans),
                                                 _p(model.xscales), _p(model.R), model.nlv, _p(pivot),
-                                                _p(out), out.shape[1]), "scores_dev")
+                                                _p(out), _ld(out)), "scores_dev")
         return out
     _lib.check(_lib.lib().jcb200_xmul_dev(_p(X), X.shape[1], n, model.p, _p(model.xmeans),
                                           _p(model.xscales), _p(model.R), model.p, model.nlv, None,

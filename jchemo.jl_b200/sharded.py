@@ -53,3 +53,92 @@ def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, pac
         dev.scores_dev(X, n_local, model, pivot=pivot)
     dev.weights_dev(w, n_local, model)
     return model
+
+
+def chunk_bounds(n):
+    """Row chunks of the streamed host fit: n/8 rows each, the last one cut again into n/16, n/32, n/32 (what is
+    left to do when the last byte has arrived is K1 on 1/32 of the rows); boundaries are even."""
+    if n < 400000:
+        return [0, n]
+    chunk = dev.even_up(-(-n // 8))
+    b = [0]
+    while n - b[-1] > chunk:
+        b.append(b[-1] + chunk)
+    rest = n - b[-1]
+    half, quarter = dev.even_up(rest // 2), dev.even_up(rest // 4)
+    if quarter >= 4096:
+        b += [b[-1] + half, b[-1] + half + quarter]
+    b.append(n)
+    return b
+
+
+_side = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=device)
+    return _side[key]
+
+
+def fit_sharded_from_host(hX, hY, hw, X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None,
+                          hT=None):
+    """fit_sharded with this rank's rows in page-locked HOST tensors hX [p, n_local], hY [q, n_local]
+    (hw [n_local] or None); X, Y, w are the device buffers they are streamed into.  The rows go over in
+    chunks on a side stream and K1 runs on chunk i while chunk i+1 is in flight, the partial Grams
+    accumulating in `packed`; the pivot comes from rank 0's first chunk.  The host paces the pipeline — the
+    copy of chunk i+1 is issued after the kernel on chunk i — because a copy queued ahead of a kernel was
+    observed to hold the kernel back.  With hT [nlv, n_local] (page-locked) the scores are
+    copied back in four row blocks, each under the next block's K5."""
+    p, q = X.shape[0], Y.shape[0]
+    if pivot is None:
+        pivot = torch.empty(p + q + 1, dtype=torch.float64, device=X.device)
+    if packed is None:
+        packed = torch.empty(dev.packed_len(p, q), dtype=torch.float64, device=X.device)
+    main, side = torch.cuda.current_stream(X.device), _side_stream(X.device)
+    b = chunk_bounds(n_local)
+    side.wait_stream(main)
+
+    def issue(ci):
+        r0, r1 = b[ci], b[ci + 1]
+        dev.copy_rows_async(X[:, r0:r1], hX[:, r0:r1], r1 - r0, side)
+        dev.copy_rows_async(Y[:, r0:r1], hY[:, r0:r1], r1 - r0, side)
+        with torch.cuda.stream(side):
+            if hw is not None and ci == 0:
+                w[:n_local].copy_(hw, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+
+    ev = issue(0)
+    for ci in range(len(b) - 1):
+        r0, r1 = b[ci], b[ci + 1]
+        ev.synchronize()
+        Xc, Yc = X[:, r0:r1], Y[:, r0:r1]
+        if ci == 0:
+            dev.pivot_dev(Xc, Yc, r1 - r0, pivot)
+            broadcast_pivot(pivot, group)
+        dev.gram_dev(Xc, Yc, None if w is None or hw is None else w[r0:r1], r1 - r0, pivot, packed,
+                     accumulate=ci > 0)
+        if ci + 2 < len(b):
+            ev = issue(ci + 1)
+    reduce_packed(packed, group)
+    dev.solve_dev(packed, pivot, model, scal)
+    if model.nlv > 0:
+        if hT is None or n_local < 400000:
+            dev.scores_dev(X, n_local, model, pivot=pivot)
+            if hT is not None:
+                hT.copy_(model.T[:model.nlv, :n_local], non_blocking=True)
+        else:
+            blk = dev.even_up(-(-n_local // 4))
+            for r0 in range(0, n_local, blk):
+                r1 = min(n_local, r0 + blk)
+                dev.scores_dev(X[:, r0:r1], r1 - r0, model, out=model.T[:, r0:r1], pivot=pivot)
+                done = torch.cuda.Event()
+                done.record(main)
+                side.wait_event(done)
+                dev.copy_rows_async(hT[:, r0:r1], model.T[:model.nlv, r0:r1], r1 - r0, side)
+            main.wait_stream(side)
+    dev.weights_dev(w if hw is not None else None, n_local, model)
+    return model

@@ -461,3 +461,42 @@ def test_lvloop_forms(jc, n, p, q, nlv, scal):
     assert relerr(jc.predict(fm, X[:64]).pred, oracle.predict(ref, X[:64])) < TOL
     np.testing.assert_allclose(np.linalg.norm(fm.W, axis=0), 1, atol=1e-12)
     assert np.abs(fm.P[:, :lead].T @ fm.R[:, :lead] - np.eye(lead)).max() < TOL
+
+
+def test_streamed_host_fit_matches_resident_fit(jc):
+    """sharded.fit_sharded_from_host (rows streamed in chunks from page-locked host memory under K1, scores
+    copied back in row blocks) against the same fit on device-resident inputs."""
+    import torch
+    from jchemo_b200 import device as dev, sharded
+    n, p, q, nlv = 400_001, 48, 3, 7
+    torch.cuda.set_device(0)
+    dev.init(0)
+    dev.use_current_stream()
+    try:
+        X = dev.colmajor_empty(n, p)
+        Y = dev.colmajor_empty(n, q)
+        dev.fill_uniform(X, n, 1)
+        dev.fill_uniform(Y, n, 2)
+        hX = torch.empty((p, n), dtype=torch.float64).pin_memory()
+        hY = torch.empty((q, n), dtype=torch.float64).pin_memory()
+        hX.copy_(X[:, :n])
+        hY.copy_(Y[:, :n])
+        m0 = dev.DeviceModel(n, p, q, nlv)
+        sharded.fit_sharded(X, Y, None, n, m0)
+        X2 = torch.zeros_like(X)
+        Y2 = torch.zeros_like(Y)
+        m1 = dev.DeviceModel(n, p, q, nlv)
+        hT = torch.empty((nlv, n), dtype=torch.float64).pin_memory()
+        assert len(sharded.chunk_bounds(n)) - 1 == 10
+        sharded.fit_sharded_from_host(hX, hY, None, X2, Y2, None, n, m1, hT=hT)
+        torch.cuda.synchronize()
+        s = torch.sign((m0.W[:nlv] * m1.W[:nlv]).sum(dim=1))
+        T0 = (m0.T[:nlv, :n] * s[:, None]).cpu().numpy()
+        assert relerr(hT.numpy(), T0) < 1e-11
+        assert relerr(m1.T[:nlv, :n].cpu().numpy(), T0) < 1e-11
+        assert relerr(m1.xmeans.cpu().numpy(), m0.xmeans.cpu().numpy()) < 1e-13
+        B0 = (m0.R[:nlv].T @ m0.C[:nlv]).cpu().numpy()
+        B1 = (m1.R[:nlv].T @ m1.C[:nlv]).cpu().numpy()
+        assert relerr(B1, B0) < 1e-11
+    finally:
+        dev.use_own_stream()
