@@ -170,6 +170,13 @@ struct Carver {
 };
 
 static inline int64_t even_up(int64_t v) { return (v + 1) & ~(int64_t)1; }
+// row count from which the host paths stream their rows in chunks (JCB_CHUNK_MIN_ROWS lets the tests exercise
+// the chunked paths on small inputs)
+static int64_t chunk_min_rows() {
+    const char* e = getenv("JCB_CHUNK_MIN_ROWS");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (int64_t)v : 400000;
+}
 
 // K5 on the rows the Gram was built from: K1's centring decision (last element of the pivot buffer) lets
 // the score pass skip the per-element centring when every column is well scaled about zero
@@ -747,13 +754,13 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     // the last byte has arrived is K1 on 1/32 of the rows instead of 1/8.
     std::vector<int64_t> bounds;              // chunk ci covers rows [bounds[ci], bounds[ci+1])
     bounds.push_back(0);
-    if (n >= 400000) {
+    if (n >= chunk_min_rows()) {
         int64_t chunk = (n + 7) / 8;
         chunk = (chunk + 1) & ~(int64_t)1;              // shards stay 16-byte aligned
         while (n - bounds.back() > chunk) bounds.push_back(bounds.back() + chunk);
         const int64_t rest = n - bounds.back();
         const int64_t half = ((rest / 2) + 1) & ~(int64_t)1, quarter = ((rest / 4) + 1) & ~(int64_t)1;
-        if (quarter >= 4096) {
+        if (quarter >= 4096 || (quarter >= 2 && chunk_min_rows() < 400000)) {
             bounds.push_back(bounds.back() + half);
             bounds.push_back(bounds.back() + quarter);
         }
@@ -783,7 +790,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
                          d_sumw));
     // Scores: into page-locked T the score pass runs in four row blocks, each block's device-to-host copy
     // (copy stream) under the next block's K5, so the PCIe transfer of T starts a quarter pass after the solve
-    const bool pipeT = nlv > 0 && n >= 400000 && is_pinned(T);
+    const bool pipeT = nlv > 0 && n >= chunk_min_rows() && is_pinned(T);
     if (pipeT) {
         int64_t blk = (n + 3) / 4;
         blk = (blk + 1) & ~(int64_t)1;
@@ -913,7 +920,7 @@ static int pipeline_rows(Ctx* c, const double* X, int64_t ldx, int64_t m, int64_
     return 0;
 }
 static int64_t pipeline_chunk(int64_t m) {
-    if (m < 400000) return even_up(m);
+    if (m < chunk_min_rows()) return even_up(m);
     return even_up((m + 7) / 8);
 }
 }  // extern "C++"

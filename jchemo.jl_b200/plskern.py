@@ -8,6 +8,7 @@ libjchemo_b200.so on the GPU through the C ABI; this file only coerces shapes
 exceptions.  There is no CPU fallback.
 """
 import ctypes as C
+import os
 import weakref
 from collections import namedtuple
 from dataclasses import dataclass
@@ -69,7 +70,7 @@ def _out_empty(shape):
     (jcb200_host_alloc): the device-to-host copy of the scores then runs at PCIe speed; the block goes
     back to the pool when the array is garbage collected.  Falls back to ordinary memory."""
     nbytes = int(np.prod(shape)) * 8
-    if nbytes >= (1 << 22):
+    if nbytes >= int(os.environ.get("JCB_PINNED_MIN_BYTES", 1 << 22)) and nbytes > 0:
         lib = _lib.lib()
         p = lib.jcb200_host_alloc(nbytes)
         if p:

@@ -500,3 +500,36 @@ def test_streamed_host_fit_matches_resident_fit(jc):
         assert relerr(B1, B0) < 1e-11
     finally:
         dev.use_own_stream()
+
+
+def test_chunked_host_paths_on_small_inputs(jc, monkeypatch):
+    """The row-chunk machinery of the host paths (chunked H2D under K1 with the cut last chunk, row-block
+    score copy-back, three-stream pipelines of predict / transform / xfit) normally starts at 400 000 rows;
+    JCB_CHUNK_MIN_ROWS forces it on a small ragged input, with page-locked outputs, against the oracle."""
+    monkeypatch.setenv("JCB_CHUNK_MIN_ROWS", "64")
+    monkeypatch.setenv("JCB_PINNED_MIN_BYTES", "1")
+    n, p, q, nlv, m = 1003, 37, 3, 6, 517
+    X = synth.synth_matrix(1, n, p) + np.arange(p)[None, :]
+    Y = synth.synth_matrix(2, n, q) + X[:, :q]
+    w = synth.synth_weights(n, uniform=False)
+    Xnew = synth.synth_matrix(4, m, p) + np.arange(p)[None, :]
+    for scal in (False, True):
+        fm = jc.plskern(X, Y, w, nlv=nlv, scal=scal)
+        ref = oracle.plskern(X, Y, w, nlv=nlv, scal=scal)
+        s = oracle.sign_align(ref, fm)
+        assert relerr(fm.T * s, ref.T) < TOL
+        assert relerr(fm.weights, ref.weights) < 1e-14
+        assert relerr(jc.transform(fm, Xnew) * s, oracle.transform(ref, Xnew)) < TOL
+        pr = jc.predict(fm, Xnew, nlv=range(0, nlv + 1)).pred
+        rr = oracle.predict(ref, Xnew, nlv=range(0, nlv + 1))
+        assert max(relerr(a, b) for a, b in zip(pr, rr)) < TOL
+        assert relerr(jc.predict(fm, Xnew, nlv=3).pred, oracle.predict(ref, Xnew, nlv=3)) < TOL
+        assert relerr(jc.xfit(fm, Xnew, nlv=4), oracle.xfit(ref, Xnew, nlv=4)) < TOL
+        E = jc.xresid(fm, Xnew)
+        assert np.abs(E - oracle.xresid(ref, Xnew)).max() < 1e-9 * np.abs(Xnew).max()
+    # plskern!: the centred / scaled X and Y come back through the same chunked path
+    Xb, Yb = np.asfortranarray(X.copy()), np.asfortranarray(Y.copy())
+    jc.plskern_bang(Xb, Yb, w, nlv=nlv, scal=True)
+    Xr, Yr = X.copy(order="F"), Y.copy(order="F")
+    oracle.plskern_bang(Xr, Yr, w, nlv=nlv, scal=True)
+    assert relerr(Xb, Xr) < 1e-12 and relerr(Yb, Yr) < 1e-12
