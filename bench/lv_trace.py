@@ -14,8 +14,9 @@ torch.cuda.synchronize()
 raw = C.CDLL(os.environ["JCB_LIB"])
 buf = (C.c_longlong * 16)()
 raw.jcb200_debug_lv_trace(buf)
-names = ["M=XtY'XtY", "eig squaring", "v refine", "w=XtY v", "dots+r", "zp matvec + u", "cluster.sync", "tt,c", "deflate+store", "loop top"]
-tot = sum(buf[i] for i in range(10))
+names = ["A: M partial, exchange, sum", "eigenvector", "-", "B: sum of partials + sync (after wait)", "C: r, gather, u, wait", "D: matvec + send", "D: wait", "tt, c", "-", "deflate + store",
+         "B: w~ + sync", "B: dots + send", "B: wait"]
+tot = sum(buf[i] for i in range(13))
 for i, nm in enumerate(names):
-    print(f"{nm:16s} {buf[i]:10d} cyc  {buf[i]/1965e3:8.3f} ms  {100*buf[i]/max(tot,1):5.1f}%")
+    print(f"{nm:40s} {buf[i]:10d} cyc  {buf[i]/1965e3:8.3f} ms  {100*buf[i]/max(tot,1):5.1f}%")
 print("total", tot/1965e3, "ms")

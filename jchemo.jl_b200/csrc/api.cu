@@ -852,6 +852,17 @@ template <class Compute, class CopyOut>
 static int pipeline_rows(Ctx* c, const double* X, int64_t ldx, int64_t m, int64_t p, double* dX, int64_t ld,
                          int64_t chunk, Compute compute, CopyOut copy_out) {
     cudaStream_t st = c->stream, cs = c->copy_stream, os = c->out_stream;
+    // an error return must not leave copies from / into the caller's arrays in flight
+    struct DrainOnError {
+        cudaStream_t a, b, c;
+        bool ok = false;
+        ~DrainOnError() {
+            if (ok) return;
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+            cudaStreamSynchronize(c);
+        }
+    } drain{st, cs, os};
     // JCB_PIPE_TRACE=1: per-chunk completion times of the three legs on stderr (debugging aid)
     static const bool trace = getenv("JCB_PIPE_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
@@ -917,6 +928,7 @@ static int pipeline_rows(Ctx* c, const double* X, int64_t ldx, int64_t m, int64_
         }
         for (auto e : tev) cudaEventDestroy(e);
     }
+    drain.ok = true;
     return 0;
 }
 static int64_t pipeline_chunk(int64_t m) {

@@ -131,9 +131,13 @@ __device__ __forceinline__ void eig_dominant_warp_q(const int q, const double* _
                                                     double* __restrict__ v_out, const int lane) {
     switch (q) {
 #define JCB_EIG(Q) case Q: eig_dominant_warp<Q>(M_s, bufA, bufB, v_out, lane); break;
+#ifdef JCB_EIG_ONLY_Q
+        JCB_EIG(JCB_EIG_ONLY_Q)          // code-size experiment: a single instantiation
+#else
         JCB_EIG(2) JCB_EIG(3) JCB_EIG(4) JCB_EIG(5) JCB_EIG(6) JCB_EIG(7) JCB_EIG(8)
         JCB_EIG(9) JCB_EIG(10) JCB_EIG(11) JCB_EIG(12) JCB_EIG(13) JCB_EIG(14)
         JCB_EIG(15) JCB_EIG(16)
+#endif
 #undef JCB_EIG
         default: break;
     }

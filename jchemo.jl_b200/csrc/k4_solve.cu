@@ -517,14 +517,15 @@ lvloop_kernel(const LvParams prm) {
 //   A  partial M = XtY_c' XtY_c (upper triangle)            -> M, then v = dominant eigenvector (every CTA)
 //   B  partial d~ = P_c' w~_c and |w~_c|^2, w~ = XtY v       -> d~, nrm   (w is normalised together with r)
 //   C  r_c = (w~_c - R_c d~)/nrm all-gathered, partial u = XtY_c' r_c
-//   D  zp_c = XtX[c,:] r (XtX slice in shared memory when GS), per-warp partials of tt = r'zp
+//   D  zp_c = XtX[c,:] r (XtX slice in shared memory when GS), per-CTA partials of tt = r'zp
 // then c = u/tt, P_c = zp_c/tt, XtY_c -= zp_c c' locally.  Buffers and barriers need no double-buffering:
 // a CTA can only send exchange k+1 after it has completed exchange k, which needs every peer's part of k,
 // which each peer sends (behind a block barrier) after it has consumed its buffer of exchange k-1.
 constexpr int LV16_CLUSTER = 16;
+static_assert(LV_THREADS / 32 == LV16_CLUSTER, "warp w sends to CTA w: one warp per CTA of the cluster");
 
 struct LvdLayout {
-    int pe, sp, xs, Ps, Rs, w, r, zp, rfull, exA, exB, exU, exD, M, A, B, v, c, d, g, total;   // doubles
+    int pe, sp, xs, Ps, Rs, w, r, zp, rfull, exA, exB, exU, exD, M, A, B, v, c, d, red, g, total;   // doubles
 };
 __host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, bool gs) {
     LvdLayout L;
@@ -543,13 +544,14 @@ __host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, 
     L.exA = o; o += ev(LV16_CLUSTER * nt);
     L.exB = o; o += ev(LV16_CLUSTER * (nlv + 1));
     L.exU = o; o += ev(LV16_CLUSTER * q);
-    L.exD = o; o += LV16_CLUSTER * 16;
+    L.exD = o; o += LV16_CLUSTER;
     L.M = o; o += ev(q * q);
     L.A = o; o += ev(q * q);
     L.B = o; o += ev(q * q);
     L.v = o; o += ev(q);
     L.c = o; o += ev(q);
     L.d = o; o += ev(nlv + 1);
+    L.red = o; o += 32;
     L.g = o; o += gs ? per * L.pe : 0;
     L.total = o;
     return L;
@@ -600,12 +602,13 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
     double* v_s = sm + L.v;
     double* c_s = sm + L.c;
     double* d_s = sm + L.d;
+    double* red = sm + L.red;
     double* g_s = sm + L.g;
     const int64_t P64 = p;
     const uint32_t barA = smem_u32(&bars[0]), barB = smem_u32(&bars[1]), barC = smem_u32(&bars[2]),
                    barD = smem_u32(&bars[3]), barB2 = smem_u32(&bars[4]);
     const uint32_t bytesA = (uint32_t)(ncta * nt * 8), bytesC = (uint32_t)((p + ncta * q) * 8),
-                   bytesD = (uint32_t)(ncta * 16 * 8);
+                   bytesD = (uint32_t)(ncta * 8);
 
     if (tid == 0) {
         for (int b = 0; b < 5; ++b) mbar_init(&bars[b], 1);
@@ -639,8 +642,8 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
     __syncthreads();
     cluster.sync();     // every CTA is running and its barriers are initialised before the first remote store
 
-    // partial dots of the w~ slice with the P slice columns j < a and with itself (j == a), sent to slot
-    // [rank] of every CTA's exB, signalling `bar` there
+    // partial dots of the w~ slice with the P slice columns j < a and with itself (j == a) -> d_s (local), then
+    // sent to slot [rank] of every CTA's exB, signalling `bar` there.
     auto dots_and_send = [&](const int a, const uint32_t bar) {
         for (int j0 = warp; j0 <= a; j0 += 4 * nwarp) {
             double acc[4];
@@ -658,13 +661,19 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
 #pragma unroll
                 for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
             }
-            if (lane < ncta) {
-                const uint32_t rb = mapa_u32(bar, lane);
+            if (lane == 0) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (j0 + u * nwarp <= a)
-                        st_async_f64(mapa_u32(smem_u32(exB + rank * nd + j0 + u * nwarp), lane), acc[u], rb);
+                    if (j0 + u * nwarp <= a) d_s[j0 + u * nwarp] = acc[u];
             }
+        }
+        __syncthreads();
+        if (tid <= a) {
+            // thread j carries dot j to every CTA (and later replaces d_s[j] by the sum over the CTAs itself)
+            const double val = d_s[tid];
+            const uint32_t dst = smem_u32(exB + rank * nd + tid);
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(bar, cta));
         }
     };
 
@@ -690,6 +699,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
                 }
                 for (; k < nsl; ++k) s0 += ci[k] * cj[k];
                 const double val = (s0 + s1) + (s2 + s3);
+                // one destination CTA per st.async instruction (the lanes carry the entries of the triangle)
                 const uint32_t dst = smem_u32(exA + rank * nt + tid);
 #pragma unroll
                 for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barA, cta));
@@ -720,9 +730,12 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
             w_s[tid] = t;
         }
         __syncthreads();
+        LV_MARK(10);
         dots_and_send(a, barB);
+        LV_MARK(11);
         if (tid <= a) {
             mbar_wait(&bars[1], par);
+            LV_MARK(12);
             if (tid == 0 && more) mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * (a + 2) * 8));
             double v[ncta];
 #pragma unroll
@@ -777,8 +790,11 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
             double s = 0.0;
             for (int i = lane; i < nsl; i += 32) s += xs[j * sp + i] * r_s[i];
             s = warp_sum(s);
-            if (lane < ncta) st_async_f64(mapa_u32(smem_u32(exU + rank * q + j), lane), s, mapa_u32(barC, lane));
+            if (lane == 0) c_s[j] = s;
         }
+        __syncthreads();
+        if (lane < q)
+            st_async_f64(mapa_u32(smem_u32(exU + rank * q + lane), warp), c_s[lane], mapa_u32(barC, warp));
         mbar_wait(&bars[2], par);       // the whole r and the partial u's have landed
         LV_MARK(4);
         // ---------------------------------------------------------------- D: zp slice = XtX[lo:hi, :] r
@@ -834,7 +850,12 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
                     if (two) zp_s[i2] = z2;
                 }
             }
-            if (lane < ncta) st_async_f64(mapa_u32(smem_u32(exD + rank * 16 + warp), lane), ttw, mapa_u32(barD, lane));
+            if (lane == 0) red[warp] = ttw;
+        }
+        __syncthreads();
+        {
+            const double ttc = warp_sum(lane < nwarp ? red[lane] : 0.0);     // every warp, same order
+            if (lane == 0) st_async_f64(mapa_u32(smem_u32(exD + rank), warp), ttc, mapa_u32(barD, warp));
         }
         LV_MARK(5);
         mbar_wait(&bars[3], par);
@@ -846,11 +867,8 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
         // ---------------------------------------------------------------- tt, c, deflate, store
         double tt;
         {
-            // 256 per-warp partials, summed in the same order by every warp of every CTA
-            double s = 0.0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += exD[lane * 8 + u];
-            tt = warp_sum(s);
+            // 16 per-CTA partials, summed in the same order by every warp of every CTA
+            tt = warp_sum(lane < ncta ? exD[lane] : 0.0);
         }
         // tt == 0 (r = 0: XtY vanished, more LVs asked than the data carry): the reference divides 0/0;
         // here the LV is inert (c = 0, P = 0) so predictions stay finite
