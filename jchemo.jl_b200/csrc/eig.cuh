@@ -47,7 +47,8 @@ __device__ __forceinline__ void eig_dominant_warp(const double* __restrict__ M_s
         __syncwarp();
         return;
     }
-    const double itr = 1.0 / tr;
+    // start from M scaled by the exact power of two that brings its trace into [1, 2) (no division)
+    const double itr = __hiloint2double((2046 - ((__double2hiint(tr) >> 20) & 0x7ff)) << 20, 0);
     for (int e = lane; e < Q * Q; e += 32) bufA[e] = M_s[e] * itr;
     __syncwarp();
     double* cur = bufA;
@@ -114,13 +115,24 @@ __device__ __forceinline__ void eig_dominant_warp(const double* __restrict__ M_s
         tau_prev = tau;
         scl_prev = scl;
     }
-    int best = 0;
-    double bd = cur[0];
+    // column with the largest diagonal entry: all loads first, then a pairwise tournament (ties keep the lower index)
+    double bd[Q];
+    int bi[Q];
 #pragma unroll
-    for (int d = 1; d < Q; ++d) {
-        const double x = cur[d * Q + d];
-        if (x > bd) { bd = x; best = d; }
+    for (int d = 0; d < Q; ++d) {
+        bd[d] = cur[d * Q + d];
+        bi[d] = d;
     }
+#pragma unroll
+    for (int w2 = 1; w2 < Q; w2 <<= 1) {
+#pragma unroll
+        for (int d = 0; d + w2 < Q; d += 2 * w2)
+            if (bd[d + w2] > bd[d]) {
+                bd[d] = bd[d + w2];
+                bi[d] = bi[d + w2];
+            }
+    }
+    const int best = bi[0];
     if (lane < Q) v_out[lane] = cur[lane * Q + best];
     __syncwarp();
 }
