@@ -105,3 +105,47 @@ def test_oracle_xfit_and_locwlv_properties():
     glob = oracle.predict(oracle.plskern(X, Y, nlv=3), Xq, nlv=range(0, 4))
     for a in range(4):
         assert np.allclose(loc[a], glob[a], atol=1e-12)
+
+
+def _header_prototypes():
+    """name -> list of C parameter types (names stripped) from include/jchemo_b200.h."""
+    text = open(os.path.join(ROOT, "include", "jchemo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|void|const char\s*\*|void\s*\*)\s*(jcb200_\w+)\s*\(([^)]*)\)\s*;", text):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        types = []
+        for p in params:
+            p = re.sub(r"\s+", " ", p)
+            p = re.sub(r"\s*\w+$", "", p) if not p.endswith("*") else p     # drop the parameter name
+            types.append(p.replace(" *", "*").strip())
+        protos[m.group(1)] = types
+    return protos
+
+
+_C_TO_JULIA = {
+    "const double*": {"Ptr{Float64}", "Ptr{Cdouble}"}, "double*": {"Ptr{Float64}", "Ptr{Cdouble}"},
+    "int64_t": {"Int64"}, "int32_t": {"Int32", "Cint"}, "int": {"Cint", "Int32"},
+    "int32_t*": {"Ref{Int32}", "Ptr{Int32}", "Ptr{Cint}"}, "const int*": {"Ptr{Cint}", "Ptr{Int32}"},
+    "const int32_t*": {"Ptr{Cint}", "Ptr{Int32}"},
+    "const int64_t*": {"Ptr{Int64}"}, "double* const*": {"Ptr{Ptr{Float64}}"}, "void*": {"Ptr{Cvoid}"},
+}
+
+
+def test_julia_ccall_signatures_match_the_header():
+    """Julia cannot run in this image, so the `ccall` module is checked statically: every call names a
+    declared entry point and passes exactly the header's parameter types, in order."""
+    protos = _header_prototypes()
+    src = open(os.path.join(ROOT, "jchemo.jl_b200", "julia", "JchemoB200", "src", "JchemoB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(jcb200_\w+),\s*LIB\),\s*(\w+),\s*\(([^)]*)\)", src)
+    assert len(calls) >= 10
+    for name, ret, argt in calls:
+        assert name in protos, f"{name} is not declared in include/jchemo_b200.h"
+        jl = [t.strip() for t in argt.replace("\n", " ").split(",") if t.strip()]
+        ct = protos[name]
+        assert len(jl) == len(ct), f"{name}: Julia passes {len(jl)} arguments, the header declares {len(ct)}"
+        for k, (j, c) in enumerate(zip(jl, ct)):
+            assert c in _C_TO_JULIA, f"{name}: unmapped C type {c!r}"
+            assert j in _C_TO_JULIA[c], f"{name}: argument {k + 1} is {j} in Julia but {c} in the header"
