@@ -771,13 +771,23 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
     phase_begin_on(c, JCB200_T_H2D, cs);
     if (w) JCB_TRY(h2d_2d(c, dw, ld, w, n, n, 1, cs));
-    for (int ci = 0; ci < nchunks; ++ci) {
+    // Host-paced, one copy ahead: K1 on chunk i is enqueued when its rows have landed, right after the copy of
+    // chunk i+1 has been issued.  With every copy queued up front a kernel enqueued behind them may not start
+    // before the LAST copy has finished (observed on the streaming paths, see pipeline_rows); one copy ahead
+    // bounds that to one chunk, keeps the link busy, and the last chunks are the small ones.
+    auto issue_chunk = [&](int ci) -> int {
         const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
         JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
         JCB_TRY(h2d_2d(c, dY + r0, ld, Y + r0, ldy, nr, q, cs));
         if (ci == nchunks - 1) phase_end_on(c, JCB200_T_H2D, cs);
         JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
-        JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1 + (ci & 1)], 0));
+        return 0;
+    };
+    JCB_TRY(issue_chunk(0));
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
+        JCB_CUDA(cudaEventSynchronize(c->chunk_ev[1 + (ci & 1)]));
+        if (ci + 1 < nchunks) JCB_TRY(issue_chunk(ci + 1));
         if (ci == 0) {
             phase_begin(c, JCB200_T_PIVOT);
             JCB_TRY(launch_pivot(c, dX, ld, dY, ld, nr, p, q, d_pivot));
