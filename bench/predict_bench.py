@@ -27,7 +27,7 @@ for name, fn, by, fl in [
     ("predict_sweep_0_%d" % a.nlv, lambda: dev.predict_sweep_dev(Xn, a.m, model, 0, a.nlv, pred),
      8.0 * (a.m * a.p + (a.nlv + 1) * a.m * a.q), 2.0 * a.m * a.p * a.nlv + 2.0 * a.m * a.q * a.nlv),
     ("predict_single_k", lambda: dev.predict_sweep_dev(Xn, a.m, model, a.nlv, a.nlv, pred[:1]),
-     8.0 * (a.m * a.p + a.m * a.q), 2.0 * a.m * a.p * a.nlv),
+     8.0 * (a.m * a.p + a.m * a.q), 2.0 * a.m * a.p * a.q),
     ("transform_nlv%d" % a.nlv, lambda: dev.scores_dev(Xn, a.m, model, Tn),
      8.0 * (a.m * a.p + a.m * a.nlv), 2.0 * a.m * a.p * a.nlv),
 ]:

@@ -72,6 +72,7 @@ struct Ctx {
     Buf locw_ws;
     Buf solve_ws;
     Buf xmul_ws;
+    Buf coef_ws;         // B (p x q) and intercept of a single-k prediction on the device path
     const double* xmul_center_flag = nullptr;   // set around the fit's score pass: K1's centring decision (device)
     // general scratch for the host-pointer API
     Buf hX, hY, hW, hT, hSmall, hPred;

@@ -49,6 +49,8 @@ struct XmulParams {
     int64_t ldo;
     int ncol;              // real output columns in this pass
     int aligned;           // X is 16-byte aligned with even ldx: bulk copies allowed
+    int direct;            // !SWEEP: results go from the accumulator fragments straight to global memory (no
+                           // staging tile in shared memory: room for one more pipeline stage)
     const double* cflag;   // device flag of the fit (pivot[p+q]): != 1.0 = every column has mean^2 <= 64 var, so the
                            // scores may be formed as X M - mu'M (no DADD per element beside the DMMAs); else null
     // sweep epilogue
@@ -109,7 +111,8 @@ xmul_kernel(const XmulParams prm) {
     const int nstage = prm.nstage;
     unsigned char* stage_base = smem;
     double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NPT][132]
-    double* mu_s = out_s + NPT * XM_PITCH;                                        // nchunk*32
+    const bool direct = !SWEEP && prm.direct != 0;
+    double* mu_s = out_s + (direct ? 0 : NPT * XM_PITCH);                         // nchunk*32
     double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
     double* cb_s = cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0);          // NPT (+ pad): -mu'M, centre-free path
     uint64_t* full = reinterpret_cast<uint64_t*>(cb_s + 64 + 8);
@@ -293,6 +296,42 @@ xmul_kernel(const XmulParams prm) {
         };
         if (center) chunk_loop(std::true_type{});
         else chunk_loop(std::false_type{});
+        if (direct) {
+            // ---- epilogue, direct: lane (g, kk) holds rows m0 + 2g + h, columns nb*8 + 2kk (+1): for one
+            // register the eight g-lanes of a column write eight rows two apart, the h = 0 / 1 stores fill
+            // each other's gaps (merged in L2; the result is 5 % of the kernel's traffic)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = m0 + 2 * g + h;
+                double* o = prm.Out + row0 + row;
+#pragma unroll
+                for (int nb = 0; nb < NPB; ++nb) {
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const int col = nb * 8 + 2 * kk + e2;
+                        if (row < rows && col < prm.ncol) {
+                            double v = acc[h][nb][e2];
+                            if (!center) v += cb_s[col];
+                            if (prm.bias) v += prm.bias[col];
+                            o[(int64_t)col * prm.ldo] = v;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NEX; ++e) {
+                    double v = ex[h][e];                  // partial over this lane's k (kk); sum the 4 kk lanes
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int col = NP + e;
+                    if (kk == 0 && row < rows && col < prm.ncol) {
+                        if (!center) v += cb_s[col];
+                        if (prm.bias) v += prm.bias[col];
+                        o[(int64_t)col * prm.ldo] = v;
+                    }
+                }
+            }
+            continue;
+        }
         // ---- epilogue: fragments -> shared (this warp's 16 rows) -> 128-byte global rows
         if (SWEEP && tn > 0) mbar_wait(tempty, (tn - 1) & 1);     // the previous tile has been read out
 #pragma unroll
@@ -347,9 +386,25 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     constexpr int XM_PITCH = XM_MT + 4;
     constexpr int XM_THREADS = (NCW + 1 + xm_epw<SWEEP, NCW>()) * 32;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
-    const int fixed = NP * XM_PITCH * 8 + prm.nchunk * XM_KC * 8 + 128 + (64 + 8) * 8 +
-                      (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
-    int nstage = (int)(((XM_OCC == 2 ? 110 : 220) * 1024 - fixed) / stage);
+    // Results either go through a staging tile in shared memory (128-byte global rows) or straight from the
+    // accumulator fragments to global memory.  The direct form is chosen when dropping the staging tile turns a
+    // 2-stage pipeline into a 3-stage one (C2: 0.96 -> 0.875 ms: HBM and the FP64 pipe are balanced there and
+    // the deeper pipeline smooths their bursts); with 3+ stages anyway it gains nothing and its stores are
+    // slightly less efficient.  JCB_XM_DIRECT=0/1 forces one form.
+    static int direct_env = -2;
+    if (direct_env == -2) {
+        const char* e = getenv("JCB_XM_DIRECT");
+        direct_env = e ? atoi(e) : -1;
+    }
+    const int budget = (XM_OCC == 2 ? 113 : 226) * 1024;
+    const int fixed_base = prm.nchunk * XM_KC * 8 + 128 + (64 + 8) * 8 +
+                           (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) * 8 : 0);
+    const int fixed_staged = fixed_base + NP * XM_PITCH * 8;
+    const int ns_staged = std::min(4, (budget - fixed_staged) / stage), ns_direct = std::min(4, (budget - fixed_base) / stage);
+    prm.direct = 0;
+    if (!SWEEP) prm.direct = direct_env >= 0 ? (direct_env ? 1 : 0) : ((ns_staged < 3 && ns_direct > ns_staged) ? 1 : 0);
+    const int fixed = prm.direct ? fixed_base : fixed_staged;
+    int nstage = prm.direct ? ns_direct : ns_staged;
     if (nstage > 4) nstage = 4;
     if (nstage < 2) {
         if (NCW == 16) return -1000;                // wide tile does not fit: caller falls back to NCW = 8
@@ -503,6 +558,15 @@ int launch_predict_sweep(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64
         fill_ymeans_kernel<<<256, 256, 0, c->stream>>>(dymeans, m, (int)q, k_hi - k_lo + 1, dPred);
         g_launches++;
         if (cudaGetLastError() != cudaSuccess) r = 1;
+    } else if (k_lo == k_hi) {
+        // single k: the reference's own arithmetic, pred = int + X B (plskern.jl:233-234), as
+        // ymeans + (X - xmeans) B with B = coef(k): q output columns instead of k score columns — HBM-bound
+        r = ensure(c->coef_ws, (size_t)(p * q + q) * 8);
+        double* dB = (double*)c->coef_ws.p;
+        if (r == 0) r = launch_coef(c, dR, dC, dxmeans, dxscales, dymeans, dyscales, p, q, k_hi, dB, dB + p * q);
+        if (r == 0)
+            r = xmul_common(c, dX, ldx, m, p, dxmeans, nullptr, dB, p, (int)q, dymeans, dPred, m, false, nullptr,
+                            nullptr, nullptr, 0, 0, 0, nullptr);
     } else {
         r = xmul_common(c, dX, ldx, m, p, dxmeans, dxscales, dR, p, k_hi, nullptr, nullptr, 0, true, dC,
                         dyscales, dymeans, (int)q, k_lo, k_hi, dPred);

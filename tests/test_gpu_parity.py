@@ -533,3 +533,34 @@ def test_chunked_host_paths_on_small_inputs(jc, monkeypatch):
     Xr, Yr = X.copy(order="F"), Y.copy(order="F")
     oracle.plskern_bang(Xr, Yr, w, nlv=nlv, scal=True)
     assert relerr(Xb, Xr) < 1e-12 and relerr(Yb, Yr) < 1e-12
+
+
+def test_device_single_k_prediction_matches_sweep(jc):
+    """Device API: a single-k prediction (coef + narrow GEMM, the reference's own arithmetic) against the last
+    matrix of the sweep 0:k and against the oracle."""
+    import torch
+    from jchemo_b200 import device as dev, sharded
+    n, p, q, nlv, m = 5000, 70, 3, 9, 777
+    torch.cuda.set_device(0)
+    dev.init(0)
+    dev.use_current_stream()
+    try:
+        X, Y = synth.synth_matrix(1, n, p), synth.synth_matrix(2, n, q)
+        Y = Y + X[:, :q]
+        Xn = synth.synth_matrix(4, m, p)
+        dX, dY, dXn = dev.colmajor_empty(n, p), dev.colmajor_empty(n, q), dev.colmajor_empty(m, p)
+        dX[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(X.T)))
+        dY[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(Y.T)))
+        dXn[:, :m].copy_(torch.from_numpy(np.ascontiguousarray(Xn.T)))
+        model = dev.DeviceModel(n, p, q, nlv)
+        sharded.fit_sharded(dX, dY, None, n, model)
+        for k in (1, 5, nlv):
+            one = dev.predict_sweep_dev(dXn, m, model, k, k)
+            swp = dev.predict_sweep_dev(dXn, m, model, 0, k)
+            torch.cuda.synchronize()
+            a, b = one[0].cpu().numpy().T, swp[k].cpu().numpy().T
+            assert relerr(a, b) < 1e-12
+            ref = oracle.plskern(X, Y, nlv=nlv)
+            assert relerr(a, oracle.predict(ref, Xn, nlv=k)) < TOL
+    finally:
+        dev.use_own_stream()
