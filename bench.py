@@ -336,7 +336,7 @@ def main():
         "launches_timed": len(gram_ms), "share_of_step": (gram_avg / ms_step) if gram_avg else None,
     }
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N=1 only (rank 0)
         threads = os.cpu_count() or 1
         times, npver = cpu_fit_seconds(CPU_SAMPLE_ROWS, 3, 1, threads)
         sec = sum(times) / len(times)
