@@ -13,9 +13,11 @@
 //   zp = XtX r ; tt = r'zp                   (:162-164,167 without touching X)
 //   c  = XtY' r / tt                          (:165-166, XtY before deflation)
 //   XtY -= zp c' ; P_a = zp/tt                (:168-169)
-// One cluster of 8 CTAs runs the whole loop: the p x p matvec and the deflation are row-sliced across
-// the CTAs (two cluster barriers per LV), everything O(p q) is recomputed redundantly — and
-// bit-identically — by every CTA so no broadcast is needed.
+// Two forms of one persistent launch.  lvdist_kernel (q <= 16, the usual case): a 16-CTA cluster with every
+// p-vector and p-row matrix sliced over the CTAs in shared memory and four st.async / mbarrier exchanges
+// per LV.  lvloop_kernel (portable fallback, any q): a cluster of 8 CTAs, the p x p matvec and the
+// deflation row-sliced across the CTAs (one or two cluster barriers per LV), everything O(p q) recomputed
+// redundantly — and bit-identically — by every CTA so that no broadcast is needed.
 #include <cooperative_groups.h>
 
 #include "jcb_internal.cuh"
