@@ -463,7 +463,8 @@ def test_lvloop_forms(jc, n, p, q, nlv, scal):
     assert np.abs(fm.P[:, :lead].T @ fm.R[:, :lead] - np.eye(lead)).max() < TOL
 
 
-def test_streamed_host_fit_matches_resident_fit(jc):
+@pytest.mark.parametrize("weighted", [False, True])
+def test_streamed_host_fit_matches_resident_fit(jc, weighted):
     """sharded.fit_sharded_from_host (rows streamed in chunks from page-locked host memory under K1, scores
     copied back in row blocks) against the same fit on device-resident inputs."""
     import torch
@@ -477,24 +478,33 @@ def test_streamed_host_fit_matches_resident_fit(jc):
         Y = dev.colmajor_empty(n, q)
         dev.fill_uniform(X, n, 1)
         dev.fill_uniform(Y, n, 2)
+        w = hw = w2 = None
+        if weighted:
+            w = torch.empty((1, dev.even_up(n)), dtype=torch.float64, device="cuda")
+            dev.fill_uniform(w, n, 3)
+            w = (w + 0.5).reshape(-1)
+            hw = w[:n].cpu().pin_memory()
+            w2 = torch.zeros_like(w)
         hX = torch.empty((p, n), dtype=torch.float64).pin_memory()
         hY = torch.empty((q, n), dtype=torch.float64).pin_memory()
         hX.copy_(X[:, :n])
         hY.copy_(Y[:, :n])
         m0 = dev.DeviceModel(n, p, q, nlv)
-        sharded.fit_sharded(X, Y, None, n, m0)
+        sharded.fit_sharded(X, Y, w, n, m0, scal=weighted)
         X2 = torch.zeros_like(X)
         Y2 = torch.zeros_like(Y)
         m1 = dev.DeviceModel(n, p, q, nlv)
         hT = torch.empty((nlv, n), dtype=torch.float64).pin_memory()
         assert len(sharded.chunk_bounds(n)) - 1 == 10
-        sharded.fit_sharded_from_host(hX, hY, None, X2, Y2, None, n, m1, hT=hT)
+        sharded.fit_sharded_from_host(hX, hY, hw, X2, Y2, w2, n, m1, scal=weighted, hT=hT)
         torch.cuda.synchronize()
         s = torch.sign((m0.W[:nlv] * m1.W[:nlv]).sum(dim=1))
         T0 = (m0.T[:nlv, :n] * s[:, None]).cpu().numpy()
         assert relerr(hT.numpy(), T0) < 1e-11
         assert relerr(m1.T[:nlv, :n].cpu().numpy(), T0) < 1e-11
         assert relerr(m1.xmeans.cpu().numpy(), m0.xmeans.cpu().numpy()) < 1e-13
+        assert relerr(m1.xscales.cpu().numpy(), m0.xscales.cpu().numpy()) < 1e-13
+        assert relerr(m1.weights[:n].cpu().numpy(), m0.weights[:n].cpu().numpy()) < 1e-14
         B0 = (m0.R[:nlv].T @ m0.C[:nlv]).cpu().numpy()
         B1 = (m1.R[:nlv].T @ m1.C[:nlv]).cpu().numpy()
         assert relerr(B1, B0) < 1e-11
