@@ -496,9 +496,19 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     double* sw = sy + Q;
     const int nelem = 1024 + (u.kind == 2 ? 32 : 0);
     for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+        // fixed summation order (deterministic), but eight loads in flight: one dependent load per segment made
+        // this kernel a chain of memory latencies (38 us for 22 MB)
         double s = 0.0;
-        for (int sg = sbeg; sg < send; ++sg)
-            s += partials[((int64_t)sg * NCW + wu) * UNIT_STRIDE + e];
+        const double* src = partials + (int64_t)wu * UNIT_STRIDE + e;
+        int sg = sbeg;
+        for (; sg + 8 <= send; sg += 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + (int64_t)(sg + k) * NCW * UNIT_STRIDE);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[k];
+        }
+        for (; sg < send; ++sg) s += __ldcs(src + (int64_t)sg * NCW * UNIT_STRIDE);
         double* dst = nullptr;
         if (e < 1024) {
             const int blk = e >> 6, ln = (e >> 1) & 31, half = e & 1;
