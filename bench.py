@@ -263,6 +263,9 @@ def main():
 
     # ---- end to end through the host-pointer path (pinned host buffers, copies inside the timing)
     Ke = max(1, min(args.e2e_steps, K))
+    numa_node = None
+    if world > 1 and os.environ.get("JCB_NUMA_BIND", "1") != "0":
+        numa_node = sharded.bind_host_to_gpu_numa(local_rank)     # page-locked buffers local to the GPU's root
     hX = torch.empty((P, n_loc), dtype=torch.float64).pin_memory()
     hY = torch.empty((Q, n_loc), dtype=torch.float64).pin_memory()
     hX.copy_(X[:, :n_loc])
@@ -362,7 +365,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_val, "unit": "TFLOP/s", "fit_seconds": e2e_s,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "how": e2e_how,
-                "phases_ms": e2e_phases,
+                "phases_ms": e2e_phases, "numa_node_rank0": numa_node,
                 "vs_readme_seconds": (README_PLSKERN_SECONDS / e2e_s) if world == 1 else None},
         "gpu_launches": int(launches), "phases_ms_last_step": phases, "clocks": clocks,
     }

@@ -14,6 +14,30 @@ import torch.distributed as dist
 from . import device as dev
 
 
+def bind_host_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs), so that page-locked
+    buffers allocated afterwards are local to the GPU's PCIe root.  Returns the node, or None when the
+    platform does not expose one (e.g. a VM: numa_node = -1); never raises."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def shard_rows(n, rank, world):
     """Contiguous row block [lo, hi) of rank `rank`; boundaries are even so every shard of a
     column-major device buffer stays 16-byte aligned."""
