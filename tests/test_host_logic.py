@@ -113,3 +113,14 @@ def test_distributed_lv_loop_matches_oracle(n, p, q, nlv, scal):
     rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)    # noqa: E731
     assert rel(W * s, ref.W) < 1e-10 and rel(R * s, ref.R) < 1e-10 and rel(P * s, ref.P) < 1e-10
     assert rel(C * s, ref.C) < 1e-10 and rel(TT, ref.TT) < 1e-10
+
+
+def test_numa_binding_is_a_noop_without_a_gpu_or_numa_info():
+    import os
+    from jchemo_b200 import sharded
+    before = os.sched_getaffinity(0)
+    node = sharded.bind_host_to_gpu_numa(0)
+    assert node is None or isinstance(node, int)
+    if node is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
