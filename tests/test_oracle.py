@@ -141,3 +141,21 @@ def test_gridscorelv_oracle_matches_direct_loop():
         np.testing.assert_allclose([out["y1"][k], out["y2"][k]],
                                    np.sqrt(np.mean((Y[200:] - pr) ** 2, axis=0)), rtol=1e-13)
     assert list(out["nlv"]) == [0, 1, 2, 3, 4, 5]
+
+
+@pytest.mark.parametrize("scal,weighted", [(False, False), (True, True)])
+def test_plskern_agrees_with_simpls_for_one_response(scal, weighted):
+    """Third independent algorithm (SIMPLS, /root/reference/src/plssimp.jl): for q = 1 the regression
+    coefficients of every nlv coincide with kernel PLS and the scores are proportional."""
+    from oracle import simpls_ref
+    n, p, nlv = 300, 40, 8
+    X = synth.synth_matrix(1, n, p)
+    y = X[:, :5] @ np.arange(1.0, 6.0) + 0.3 * synth.synth_matrix(2, n, 1)[:, 0]
+    w = synth.synth_weights(n, uniform=not weighted)
+    a = oracle.plskern(X, y, w, nlv=nlv, scal=scal)
+    b = simpls_ref.plssimp(X, y, w, nlv=nlv, scal=scal)
+    for k in range(1, nlv + 1):
+        Ba, Bb = oracle.coef(a, nlv=k)[0], oracle.coef(b, nlv=k)[0]
+        assert np.linalg.norm(Ba - Bb) / np.linalg.norm(Ba) < 1e-9
+    cosines = np.abs(np.sum(a.T * b.T, axis=0)) / (np.linalg.norm(a.T, axis=0) * np.linalg.norm(b.T, axis=0))
+    np.testing.assert_allclose(cosines, 1.0, atol=1e-9)
