@@ -159,3 +159,22 @@ def test_plskern_agrees_with_simpls_for_one_response(scal, weighted):
         assert np.linalg.norm(Ba - Bb) / np.linalg.norm(Ba) < 1e-9
     cosines = np.abs(np.sum(a.T * b.T, axis=0)) / (np.linalg.norm(a.T, axis=0) * np.linalg.norm(b.T, axis=0))
     np.testing.assert_allclose(cosines, 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("q,scal,weighted", [(1, False, False), (3, True, True), (4, False, True)])
+def test_plskern_agrees_with_rosa(q, scal, weighted):
+    """Fourth independent algorithm (/root/reference/src/plsrosa.jl: only Y deflated, explicit projectors):
+    the same Plsr for any number of responses, up to the sign of each LV."""
+    from oracle import rosa_ref
+    n, p, nlv = 250, 30, 7
+    X = synth.synth_matrix(1, n, p)
+    Y = X[:, :q] * np.arange(1.0, q + 1.0) + X[:, 5:5 + q] + 0.2 * synth.synth_matrix(2, n, q)
+    w = synth.synth_weights(n, uniform=not weighted)
+    a = oracle.plskern(X, Y, w, nlv=nlv, scal=scal)
+    b = rosa_ref.plsrosa(X, Y, w, nlv=nlv, scal=scal)
+    s = oracle.sign_align(a, b)
+    rel = lambda u, v: np.linalg.norm(u - v) / np.linalg.norm(v)    # noqa: E731
+    assert rel(b.T * s, a.T) < 1e-9 and rel(b.W * s, a.W) < 1e-9 and rel(b.P * s, a.P) < 1e-9
+    assert rel(b.C * s, a.C) < 1e-9 and rel(b.TT, a.TT) < 1e-9 and rel(b.R * s, a.R) < 1e-9
+    for k in (1, nlv):
+        assert rel(oracle.coef(b, nlv=k)[0], oracle.coef(a, nlv=k)[0]) < 1e-9
