@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 # BASELINE.json configs[1]
 N_PER_GPU, P, Q, NLV = 1_000_000, 500, 10, 25
 README_PLSKERN_SECONDS = 8.100469      # /root/reference/README.md:91 (i9-10885H laptop), BASELINE.md §1
-CPU_SAMPLE_ROWS = 250_000              # bounded sample for the CPU arms
+CPU_SAMPLE_ROWS = int(os.environ.get("JCB_BENCH_CPU_ROWS", 250_000))    # bounded sample for the CPU arms
 
 
 def f_gram(n, p, q):

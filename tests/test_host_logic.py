@@ -124,3 +124,27 @@ def test_numa_binding_is_a_noop_without_a_gpu_or_numa_info():
     if node is None:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): exactly one JSON line on stdout
+    with the contract's keys; ranks other than 0 print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JCB_BENCH_CPU_ROWS="4000")
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "plskern_fit_fp64_tflops" and d["unit"] == "TFLOP/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    res1 = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=300)
+    assert res1.returncode == 0 and res1.stdout.strip() == ""
