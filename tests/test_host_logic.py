@@ -148,3 +148,18 @@ def test_bench_reference_arm_contract():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     res1 = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=300)
     assert res1.returncode == 0 and res1.stdout.strip() == ""
+
+
+def test_ensure_mat_coercions_mirror_the_reference():
+    """`ensure_mat` (/root/reference/src/utility.jl:544-548): Matrix stays, Vector -> n x 1, DataFrame -> Matrix;
+    the host mirror and the oracle agree, and a transposed view (Julia's Adjoint) is accepted."""
+    import pandas as pd
+    import jchemo_b200 as jc
+    from oracle import plskern_ref
+    v = np.arange(3.0)
+    M = np.arange(6.0).reshape(3, 2)
+    df = pd.DataFrame(M, columns=["a", "b"])
+    for f in (jc.ensure_mat, plskern_ref.ensure_mat):
+        assert f(v).shape == (3, 1) and f(M).shape == (3, 2) and f(M.T).shape == (2, 3)
+        out = f(df)
+        assert isinstance(out, np.ndarray) and out.shape == (3, 2) and np.array_equal(out, M)
