@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JCB200_VERSION 100 /* 0.1.0 */
+#define JCB200_VERSION 200 /* 0.2.0 */
 
 /* status codes (< 0: argument errors) */
 #define JCB200_OK 0
@@ -36,6 +36,9 @@ extern "C" {
 #define JCB200_ENODEV (-2)   /* no CUDA device, or compute capability != 10.x                      */
 #define JCB200_ENOMEM (-3)   /* device allocation failed                                           */
 #define JCB200_EALIGN (-4)   /* "_dev" pointer not 16-byte aligned or odd leading dimension         */
+#define JCB200_ENONFINITE (-5) /* X, Y or the weights contain NaN / Inf (the reference throws from LAPACK's
+                                  svd at /root/reference/src/plskern.jl:154 for q > 1 and returns an all-NaN
+                                  model for q == 1); outputs are unspecified, plskern! leaves X, Y untouched */
 
 /* number of phases reported by jcb200_last_timings (ms each, CUDA events on the library stream) */
 #define JCB200_NPHASE 10
@@ -89,6 +92,24 @@ int jcb200_host_unregister(void* ptr);
  * 3 GB) for later calls.  jcb200_host_free may be called from a finalizer thread. */
 void* jcb200_host_alloc(int64_t bytes);
 int jcb200_host_free(void* ptr);
+
+/* ---- resident matrices (device-resident data handle) ------------------------------------------
+ * The reference's workflows reuse one X: gridscorelv fits then predicts (/root/reference/src/gridscore.jl:179-180),
+ * summary(fm, X) takes the training X (/root/reference/src/plskern.jl:246-249), gridcvlv repeats over the same
+ * X, Y.  jcb200_resident_add uploads a host matrix ONCE and keys the device copy by (pointer, leading dimension,
+ * shape); every host-pointer entry point below that is handed exactly that matrix as X (or Y) then skips the
+ * host-to-device transfer.  The caller must not modify a resident matrix on the host between calls; calls that
+ * modify it themselves keep the copies consistent (plskern! centres both) or drop the entry (xfit!, xresid!).
+ * Single-device mode only (after jcb200_init_multi the sharded fit ignores the registry).  At most 16 entries. */
+int jcb200_resident_add(const double* A, int64_t lda, int64_t rows, int64_t cols);
+int jcb200_resident_drop(const double* A);
+int jcb200_resident_count(void);
+
+/* Facts about the last successful jcb200_plskern_fit of the calling thread: the number of latent variables
+ * that carry information (TT[a] > 0).  A degenerate LV — XtY deflated to exactly zero, e.g. constant y or more
+ * LVs than the data carry; the reference divides 0/0 at /root/reference/src/plskern.jl:152,166 — is returned
+ * inert (w = e_1, c = 0, P = 0), so predictions stay finite and equal those of the last informative LV. */
+int jcb200_last_fit_info(int32_t* nlv_effective);
 
 /* ---- host-pointer entry points (the drop-in path) ------------------------------------------- */
 
@@ -201,7 +222,8 @@ int jcb200_gram_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy
 
 /* K3 + K4 on the (all-reduced) packed buffer: means, scales, X'DX, X'DY, then the LV loop
  * (plskern.jl:118-126,149-175 in Gram form).  Device outputs: P,R,W p*nlv (ld p), C q*nlv, TT nlv,
- * xmeans, xscales p, ymeans, yscales q, sumw 1 (the global sum of weights).  nlv already clamped. */
+ * xmeans, xscales p, ymeans, yscales q, dsumw TWO doubles: [0] the global sum of weights, [1] 0.0 / 1.0 =
+ * the input was finite / contained NaN or Inf (the LV loop is then skipped).  nlv already clamped. */
 int jcb200_solve_dev(const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
                      int32_t nlv, int32_t scal, double* dP, double* dR, double* dW, double* dC,
                      double* dTT, double* dxmeans, double* dxscales, double* dymeans,
@@ -246,6 +268,28 @@ int jcb200_weights_dev(const double* dw, int64_t n, const double* dsumw, double*
  * global row row0 of an n_global-row matrix gets u(seed, (row0 + i) + j * n_global). */
 int jcb200_fill_uniform_dev(double* d, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed,
                             int64_t row0, int64_t n_global);
+
+/* ---- peer-memory exchange for the row-sharded fit, one process per GPU -------------
+ * The only exchange of the path is the sum of the packed partial Grams (and, before it, the pivot of rank 0).
+ * Instead of a collective library the ranks read and write each other's HBM over NVLink / NVSwitch through
+ * CUDA IPC windows: K1b's packed block is pushed, coalesced, into slot [rank] of every peer's window and a
+ * flag is raised there; the next kernel on each rank waits for its `world` flags and adds the slots in rank
+ * order (bit-identical on every rank, deterministic).  No host synchronisation, no NCCL call in the fit.
+ *   1. every rank: jcb200_comm_create(rank, world, max_packed_len, handle)   -> 64-byte IPC handle
+ *   2. exchange the handles by any means (torch.distributed.all_gather_object, a file, MPI ...)
+ *   3. every rank: jcb200_comm_connect(all_handles)                         (world * 64 bytes, rank order)
+ *   4. per fit:    jcb200_comm_pivot_dev ... jcb200_gram_dev ... jcb200_comm_allreduce_dev ... jcb200_solve_dev
+ * All ranks must issue the same sequence of comm calls. */
+#define JCB200_IPC_HANDLE_BYTES 64
+int jcb200_comm_create(int32_t rank, int32_t world, int64_t max_packed_len, void* handle_out);
+int jcb200_comm_connect(const void* all_handles);
+int jcb200_comm_destroy(void);
+/* Rank 0 computes the pivot of ITS rows (jcb200_pivot_dev) and publishes it; the other ranks fetch it out of
+ * rank 0's window.  d_pivot (p + q + 1 doubles) is valid on every rank afterwards (stream order). */
+int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
+                          int64_t p, int64_t q, double* d_pivot);
+/* d_packed (len doubles) <- sum over ranks of d_packed, in place, same bits on every rank. */
+int jcb200_comm_allreduce_dev(double* d_packed, int64_t len);
 
 /* Whole single-GPU fit on device-resident inputs (pivot, gram, solve, scores [, write-back]);
  * dT n*nlv (ld = ldt), dw_out n.  Used by bench.py for the HBM-resident `value`. */

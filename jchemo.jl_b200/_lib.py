@@ -29,6 +29,15 @@ SIGNATURES = {
     "jcb200_host_unregister": (C.c_int, [C.c_void_p]),
     "jcb200_host_alloc": (C.c_void_p, [i64]),
     "jcb200_host_free": (C.c_int, [C.c_void_p]),
+    "jcb200_resident_add": (C.c_int, [C.c_void_p, i64, i64, i64]),
+    "jcb200_resident_drop": (C.c_int, [C.c_void_p]),
+    "jcb200_resident_count": (C.c_int, []),
+    "jcb200_last_fit_info": (C.c_int, [C.POINTER(i32)]),
+    "jcb200_comm_create": (C.c_int, [i32, i32, i64, C.c_void_p]),
+    "jcb200_comm_connect": (C.c_int, [C.c_void_p]),
+    "jcb200_comm_destroy": (C.c_int, []),
+    "jcb200_comm_pivot_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
+    "jcb200_comm_allreduce_dev": (C.c_int, [C.c_void_p, i64]),
     "jcb200_plskern_fit": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32,
                                      i32, i32, C.c_void_p, i64] + [C.c_void_p] * 10 +
                            [C.POINTER(i32)]),
@@ -70,8 +79,16 @@ PHASES = ["h2d", "pivot", "gram", "reduce", "finalize", "lvloop", "scores", "wri
 _lib = None
 
 
+ENONFINITE = -5      # JCB200_ENONFINITE
+IPC_HANDLE_BYTES = 64
+
+
 class JchemoB200Error(RuntimeError):
     pass
+
+
+class NonFiniteError(JchemoB200Error, ValueError):
+    """X, Y or the weights contain NaN / Inf (the reference: ArgumentError from LAPACK's svd, plskern.jl:154)."""
 
 
 def lib():
@@ -94,7 +111,8 @@ def lib():
 def check(rc, what):
     if rc != 0:
         msg = lib().jcb200_last_error().decode("utf-8", "replace")
-        raise JchemoB200Error(f"{what} failed (status {rc}): {msg}")
+        cls = NonFiniteError if rc == ENONFINITE else JchemoB200Error
+        raise cls(f"{what} failed (status {rc}): {msg}")
 
 
 def gram_timings(k):

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjchemo_b200.so")
-SOURCES = ["api.cu", "gridscore.cu", "hostcopy.cu", "k1_gram.cu", "k4_solve.cu", "k5_xmul.cu", "k7_misc.cu", "k9_locw.cu", "k10_xfit.cu"]
+SOURCES = ["api.cu", "comm.cu", "gridscore.cu", "hostcopy.cu", "k1_gram.cu", "k4_solve.cu", "k5_xmul.cu", "k7_misc.cu", "k9_locw.cu", "k10_xfit.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
 

@@ -51,32 +51,49 @@ int ensure(Buf& b, size_t bytes) {
     return 0;
 }
 
+// Phase timers.  phase_begin/phase_end bracket ONE occurrence on the compute stream; a phase that occurs
+// several times in a call (K1 on every row chunk, K5 on every score block) is reported as the SUM of its
+// occurrences.  The *_on forms mark a SPAN on another stream (first begin .. last end): the copy legs.
 void phase_begin(Ctx* c, int ph) {
-    if (!c->ev_used[ph]) cudaEventRecord(c->ev_begin[ph], c->stream);
+    if (c->ev_open[ph]) return;
+    if (c->ev_cnt[ph] >= Ctx::PHASE_SLOTS) c->ev_cnt[ph] = Ctx::PHASE_SLOTS - 1;   // out of slots: widen the last
+    else cudaEventRecord(c->ev_begin[ph][c->ev_cnt[ph]], c->stream);
+    c->ev_open[ph] = true;
 }
 void phase_end(Ctx* c, int ph) {
-    cudaEventRecord(c->ev_end[ph], c->stream);
-    c->ev_used[ph] = true;
+    if (!c->ev_open[ph]) return;
+    cudaEventRecord(c->ev_end[ph][c->ev_cnt[ph]], c->stream);
+    c->ev_cnt[ph]++;
+    c->ev_open[ph] = false;
 }
 void phase_begin_on(Ctx* c, int ph, cudaStream_t st) {
-    if (!c->ev_used[ph]) cudaEventRecord(c->ev_begin[ph], st);
-    c->ev_used[ph] = true;
+    if (c->ev_cnt[ph] == 0 && !c->ev_open[ph]) {
+        cudaEventRecord(c->ev_begin[ph][0], st);
+        c->ev_open[ph] = true;
+    }
 }
 void phase_end_on(Ctx* c, int ph, cudaStream_t st) {
-    cudaEventRecord(c->ev_end[ph], st);
-    c->ev_used[ph] = true;
+    if (c->ev_cnt[ph] == 0 && !c->ev_open[ph]) return;
+    cudaEventRecord(c->ev_end[ph][0], st);      // re-recording moves the end of the span
+    c->ev_cnt[ph] = 1;
+    c->ev_open[ph] = false;
 }
 static void phases_reset(Ctx* c) {
-    for (int i = 0; i < JCB200_NPHASE; ++i) c->ev_used[i] = false;
+    for (int i = 0; i < JCB200_NPHASE; ++i) {
+        c->ev_cnt[i] = 0;
+        c->ev_open[i] = false;
+    }
 }
 // after the stream has been synchronised
 static void phases_collect(Ctx* c) {
     for (int i = 0; i < JCB200_NPHASE; ++i) {
         c->last_ms[i] = 0.0;
-        if (c->ev_used[i]) {
+        for (int k = 0; k < c->ev_cnt[i]; ++k) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, c->ev_begin[i], c->ev_end[i]) == cudaSuccess)
-                c->last_ms[i] = ms;
+            if (cudaEventElapsedTime(&ms, c->ev_begin[i][k], c->ev_end[i][k]) == cudaSuccess)
+                c->last_ms[i] += ms;
+            else
+                cudaGetLastError();
         }
     }
 }
@@ -113,12 +130,17 @@ static int init_ctx(Ctx* c, int device) {
     for (int i = 0; i < 4; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->pipe_ev[i], cudaEventDisableTiming));
     c->stream = c->own_stream;
     for (int i = 0; i < JCB200_NPHASE; ++i) {
-        JCB_CUDA(cudaEventCreate(&c->ev_begin[i]));
-        JCB_CUDA(cudaEventCreate(&c->ev_end[i]));
-        c->ev_used[i] = false;
+        for (int k = 0; k < Ctx::PHASE_SLOTS; ++k) {
+            JCB_CUDA(cudaEventCreate(&c->ev_begin[i][k]));
+            JCB_CUDA(cudaEventCreate(&c->ev_end[i][k]));
+        }
+        c->ev_cnt[i] = 0;
+        c->ev_open[i] = false;
         c->last_ms[i] = 0.0;
     }
     for (int i = 0; i < 3; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->blk_ev[i], cudaEventDisableTiming));
+    c->n_resident = 0;
     for (int i = 0; i < 2; ++i) JCB_CUDA(cudaEventCreateWithFlags(&c->mg_ev[i], cudaEventDisableTiming));
     c->k1_attr_set = false;
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
@@ -176,6 +198,61 @@ static int64_t chunk_min_rows() {
     const char* e = getenv("JCB_CHUNK_MIN_ROWS");
     const long long v = e ? atoll(e) : 0;
     return v > 0 ? (int64_t)v : 400000;
+}
+
+// hX / hY are about to be overwritten: the copy gridcv keeps there for reuse_xy is gone
+static inline void invalidate_cv(Ctx* c) { c->cv_hostX = c->cv_hostY = nullptr; }
+
+// ---- resident matrices (jcb200_resident_add): exact match on pointer, leading dimension and shape
+static const Ctx::Resident* resident_find(const Ctx* c, const void* host, int64_t ld, int64_t rows, int64_t cols) {
+    for (int i = 0; i < c->n_resident; ++i) {
+        const Ctx::Resident& r = c->resident[i];
+        if (r.host == host && r.ld_host == ld && r.rows == rows && r.cols == cols) return &r;
+    }
+    return nullptr;
+}
+static void resident_drop_at(Ctx* c, int i) {
+    cudaFree(c->resident[i].dev);
+    c->resident[i] = c->resident[c->n_resident - 1];
+    c->n_resident--;
+}
+static void resident_clear(Ctx* c) {
+    while (c->n_resident > 0) resident_drop_at(c, c->n_resident - 1);
+}
+
+// per-thread facts about the last fit (jcb200_last_fit_info)
+static thread_local int32_t tl_nlv_effective = 0;
+
+// ---- pivot of a streamed host fit: a strided sample over ALL rows (16 evenly spaced blocks of 64 rows), gathered
+// by the host into a small page-locked buffer and sent ahead of the first row chunk.  A pivot taken from the first
+// chunk alone is far from the mean on row-sorted or drifting data, and the exact correction of K3 then cancels
+// digits (delta^2 / sigma^2 of them).  Costs ~4 MB of transfer at C2.
+static int host_sample_pivot(Ctx* c, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t n,
+                             int64_t p, int64_t q, double* d_pivot, cudaStream_t cs) {
+    const int nblk = 16;
+    int64_t brow = 64;
+    while (brow > 2 && (size_t)nblk * brow * (p + q) * 8 > ((size_t)24 << 20)) brow >>= 1;
+    const int64_t ns = nblk * brow, stride = n / nblk;
+    const size_t bytes = (size_t)ns * (p + q) * 8;
+    if (c->pivot_host_bytes < bytes) {
+        if (c->pivot_host) cudaFreeHost(c->pivot_host);
+        c->pivot_host = nullptr;
+        c->pivot_host_bytes = 0;
+        JCB_CUDA(cudaHostAlloc(&c->pivot_host, bytes, cudaHostAllocPortable));
+        c->pivot_host_bytes = bytes;
+    }
+    JCB_TRY(ensure(c->pivot_sample, bytes));
+    double* h = (double*)c->pivot_host;
+    for (int64_t j = 0; j < p + q; ++j) {
+        const double* col = j < p ? X + j * ldx : Y + (j - p) * ldy;
+        for (int b = 0; b < nblk; ++b) memcpy(h + j * ns + b * brow, col + b * stride, (size_t)brow * 8);
+    }
+    double* d = (double*)c->pivot_sample.p;
+    JCB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cs));
+    JCB_CUDA(cudaEventRecord(c->chunk_ev[2], cs));
+    JCB_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ev[2], 0));
+    JCB_TRY(launch_pivot(c, d, ns, d + ns * p, ns, ns, p, q, d_pivot));
+    return 0;
 }
 
 // K5 on the rows the Gram was built from: K1's centring decision (last element of the pivot buffer) lets
@@ -237,6 +314,7 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
                             double* xscales, double* ymeans, double* yscales, double* w_out) {
     const int nd = g_ndev;
     const int64_t plen = packed_len(p, q);
+    double status = 0.0;        // K3's non-finite flag of device 0 (identical on every device)
     int64_t per = (n + nd - 1) / nd;
     per = (per + 1) & ~(int64_t)1;
     struct Shard {
@@ -290,9 +368,15 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_CUDA(cudaMemcpyAsync(sh[d].d_srcs, srcs, sizeof(double*) * nd, cudaMemcpyHostToDevice, c->stream));
     }
     Ctx* c0 = dev_ctx(0);
+    invalidate_cv(c0);
     phases_reset(c0);
     JCB_CUDA(cudaSetDevice(c0->device));
     phase_begin(c0, JCB200_T_TOTAL);
+    // one pivot for all shards: a strided sample over ALL rows, sent to device 0 ahead of its first chunk
+    JCB_CUDA(cudaEventRecord(c0->chunk_ev[0], c0->stream));
+    JCB_CUDA(cudaStreamWaitEvent(c0->copy_stream, c0->chunk_ev[0], 0));
+    JCB_TRY(host_sample_pivot(c0, X, ldx, Y, ldy, n, p, q, sh[0].d_pivot, c0->copy_stream));
+    JCB_CUDA(cudaEventRecord(c0->mg_ev[1], c0->stream));      // pivot ready for the peers
     // ---- every device: stream its rows in (its own PCIe link) with K1 on the chunks underneath
     for (int d = 0; d < nd; ++d) {
         Ctx* c = dev_ctx(d);
@@ -302,7 +386,7 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));
         JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
         if (d > 0) {
-            // the pivot comes from device 0's first chunk (its copies are already queued): peer copy
+            // the pivot was computed on device 0 (from the strided host sample): peer copy
             JCB_CUDA(cudaStreamWaitEvent(st, c0->mg_ev[1], 0));
             JCB_CUDA(cudaMemcpyPeerAsync(s.d_pivot, c->device, sh[0].d_pivot, c0->device, (p + q + 1) * 8, st));
         }
@@ -319,10 +403,6 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
                 JCB_TRY(h2d_2d(c, s.dY + c0r, s.ld, Y + s.r0 + c0r, ldy, nr, q, cs));
                 JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
                 JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1 + (ci & 1)], 0));
-                if (d == 0 && ci == 0) {
-                    JCB_TRY(launch_pivot(c, s.dX, s.ld, s.dY, s.ld, nr, p, q, s.d_pivot));
-                    JCB_CUDA(cudaEventRecord(c->mg_ev[1], st));      // pivot ready for the peers
-                }
                 JCB_TRY(launch_gram(c, s.dX + c0r, s.ld, s.dY + c0r, s.ld, s.dw ? s.dw + c0r : nullptr, nr, p, q,
                                     s.d_pivot, s.d_part, ci > 0));
             }
@@ -372,6 +452,7 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_CUDA(cudaMemcpyAsync(xscales, s.dxs, p * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(ymeans, s.dym, q * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(yscales, s.dys, q * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(&status, s.d_sumw + 1, 8, cudaMemcpyDeviceToHost, st));
     }
     // ---- drain every device (a device's partial buffer must outlive its peers' reduce)
     for (int d = nd - 1; d >= 0; --d) {
@@ -381,6 +462,10 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_CUDA(cudaStreamSynchronize(c->stream));
     }
     phases_collect(c0);
+    if (status != 0.0) {
+        set_error("plskern_fit: X, Y or weights contain NaN or Inf");
+        return JCB200_ENONFINITE;
+    }
     return 0;
 }
 
@@ -463,6 +548,10 @@ int jcb200_device_count(void) {
 
 void jcb200_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        comm_destroy_locked();
+    }
     for (int d = 1; d < g_ndev; ++d) destroy_ctx(&g_extra[d - 1]);
     g_ndev = 1;
     destroy_ctx(&g_ctx);
@@ -496,11 +585,18 @@ static void destroy_ctx(Ctx* c) {
     c->sched_host = nullptr;
     c->sched_host_bytes = 0;
     c->sk_p = c->sk_q = c->sk_nst = -1;
-    for (int i = 0; i < JCB200_NPHASE; ++i) {
-        cudaEventDestroy(c->ev_begin[i]);
-        cudaEventDestroy(c->ev_end[i]);
-    }
+    for (int i = 0; i < JCB200_NPHASE; ++i)
+        for (int k = 0; k < Ctx::PHASE_SLOTS; ++k) {
+            cudaEventDestroy(c->ev_begin[i][k]);
+            cudaEventDestroy(c->ev_end[i][k]);
+        }
     for (int i = 0; i < 3; ++i) cudaEventDestroy(c->chunk_ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->blk_ev[i]);
+    resident_clear(c);
+    free_buf(c->pivot_sample);
+    if (c->pivot_host) cudaFreeHost(c->pivot_host);
+    c->pivot_host = nullptr;
+    c->pivot_host_bytes = 0;
     for (int i = 0; i < 2; ++i) cudaEventDestroy(c->mg_ev[i]);
     for (int i = 0; i < Ctx::GRAM_RING; ++i) {
         cudaEventDestroy(c->gram_ev0[i]);
@@ -606,6 +702,36 @@ int jcb200_solve_dev(const double* d_packed, const double* d_pivot, int64_t p, i
     ARG_CHECK(nlv == 0 || (dP && dR && dW && dC && dTT), "solve_dev: NULL output");
     return launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans, dxscales,
                         dymeans, dyscales, dsumw);
+}
+
+// ------------------------------------------------------------------------------------ peer exchange
+int jcb200_comm_create(int32_t rank, int32_t world, int64_t max_packed_len, void* handle_out) {
+    API_PROLOGUE();
+    return comm_create_locked(c, rank, world, max_packed_len, handle_out);
+}
+
+int jcb200_comm_connect(const void* all_handles) {
+    API_PROLOGUE();
+    return comm_connect_locked(all_handles);
+}
+
+int jcb200_comm_destroy(void) {
+    API_PROLOGUE();
+    comm_destroy_locked();
+    return 0;
+}
+
+int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,
+                          int64_t q, double* d_pivot) {
+    API_PROLOGUE();
+    ARG_CHECK(dX && dY && d_pivot && n > 0 && p > 0 && q > 0 && ldx >= n && ldy >= n, "comm_pivot_dev: bad argument");
+    return comm_pivot(c, dX, ldx, dY, ldy, n, p, q, d_pivot);
+}
+
+int jcb200_comm_allreduce_dev(double* d_packed, int64_t len) {
+    API_PROLOGUE();
+    ARG_CHECK(d_packed && len > 0, "comm_allreduce_dev: bad argument");
+    return comm_allreduce(c, d_packed, len);
 }
 
 int jcb200_xmul_dev(const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
@@ -715,20 +841,30 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     if (nlv > p) nlv = (int32_t)p;
     if (nlv_out) *nlv_out = nlv;
     ARG_CHECK(nlv == 0 || (T && P && R && W && C && TT && ldt >= n), "plskern_fit: NULL output");
+    tl_nlv_effective = 0;
 
-    if (g_ndev > 1 && n >= 65536 * (int64_t)g_ndev)
-        return fit_multi_locked(X, ldx, Y, ldy, w, n, p, q, nlv, scal, writeback_xy, T, ldt, P, R, W, C, TT,
-                                xmeans, xscales, ymeans, yscales, w_out);
+    if (g_ndev > 1 && n >= 65536 * (int64_t)g_ndev) {
+        const int r = fit_multi_locked(X, ldx, Y, ldy, w, n, p, q, nlv, scal, writeback_xy, T, ldt, P, R, W, C, TT,
+                                       xmeans, xscales, ymeans, yscales, w_out);
+        if (r == 0)
+            for (int a = 0; a < nlv; ++a) tl_nlv_effective += TT[a] > 0.0;
+        return r;
+    }
+    // a matrix registered with jcb200_resident_add is already on the device: no transfer
+    const Ctx::Resident* rx = resident_find(c, X, ldx, n, p);
+    const Ctx::Resident* ry = resident_find(c, Y, ldy, n, q);
     const int64_t ld = even_up(n);
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    if (!rx) JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    if (!ry) JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    if (!rx || !ry) invalidate_cv(c);
     JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
     JCB_TRY(ensure(c->hT, (size_t)ld * (nlv > 0 ? nlv : 1) * 8));
     const size_t small_doubles = (size_t)packed_len(p, q) + (p + q) + 20 + 3 * (size_t)p * nlv +
                                  (size_t)q * nlv + nlv + 2 * (p + q) + 64;
     JCB_TRY(ensure(c->hSmall, small_doubles * 8));
-    double* dX = (double*)c->hX.p;
-    double* dY = (double*)c->hY.p;
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
+    double* dY = ry ? ry->dev : (double*)c->hY.p;
+    const int64_t ldX = rx ? rx->ld : ld, ldY = ry ? ry->ld : ld;
     double* dw = w ? (double*)c->hW.p : nullptr;
     double* dwout = (double*)c->hW.p + ld;
     double* dT = (double*)c->hT.p;
@@ -747,15 +883,26 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     double* dys = cv.take(q);
 
     cudaStream_t st = c->stream, cs = c->copy_stream;
+    // an error return must not leave copies from / into the caller's arrays in flight
+    struct DrainOnError {
+        cudaStream_t a, b;
+        bool ok = false;
+        ~DrainOnError() {
+            if (ok) return;
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+        }
+    } drain{st, cs};
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
     // ---- rows are streamed in chunks: the copy of chunk i+1 (copy stream) overlaps K1 on chunk i
-    // (compute stream); the partial Grams accumulate in the packed buffer.  The pivot comes from chunk 0.
+    // (compute stream); the partial Grams accumulate in the packed buffer.
     // Chunks of n/8 rows, the last one cut again into n/16, n/32, n/32: what is left to do on the device when
     // the last byte has arrived is K1 on 1/32 of the rows instead of 1/8.
     std::vector<int64_t> bounds;              // chunk ci covers rows [bounds[ci], bounds[ci+1])
     bounds.push_back(0);
-    if (n >= chunk_min_rows()) {
+    const bool chunked = !rx && n >= chunk_min_rows();
+    if (chunked) {
         int64_t chunk = (n + 7) / 8;
         chunk = (chunk + 1) & ~(int64_t)1;              // shards stay 16-byte aligned
         while (n - bounds.back() > chunk) bounds.push_back(bounds.back() + chunk);
@@ -771,6 +918,12 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));      // copies must not overtake earlier work on `st`
     JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
     phase_begin_on(c, JCB200_T_H2D, cs);
+    // the pivot of a streamed fit comes from a strided sample over all rows, sent ahead of the first chunk
+    if (chunked) {
+        phase_begin(c, JCB200_T_PIVOT);
+        JCB_TRY(host_sample_pivot(c, X, ldx, Y, ldy, n, p, q, d_pivot, cs));
+        phase_end(c, JCB200_T_PIVOT);
+    }
     if (w) JCB_TRY(h2d_2d(c, dw, ld, w, n, n, 1, cs));
     // Host-paced, one copy ahead: K1 on chunk i is enqueued when its rows have landed, right after the copy of
     // chunk i+1 has been issued.  With every copy queued up front a kernel enqueued behind them may not start
@@ -778,8 +931,8 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     // bounds that to one chunk, keeps the link busy, and the last chunks are the small ones.
     auto issue_chunk = [&](int ci) -> int {
         const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
-        JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
-        JCB_TRY(h2d_2d(c, dY + r0, ld, Y + r0, ldy, nr, q, cs));
+        if (!rx) JCB_TRY(h2d_2d(c, dX + r0, ldX, X + r0, ldx, nr, p, cs));
+        if (!ry) JCB_TRY(h2d_2d(c, dY + r0, ldY, Y + r0, ldy, nr, q, cs));
         if (ci == nchunks - 1) phase_end_on(c, JCB200_T_H2D, cs);
         JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
         return 0;
@@ -787,46 +940,52 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_TRY(issue_chunk(0));
     for (int ci = 0; ci < nchunks; ++ci) {
         const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
-        JCB_CUDA(cudaEventSynchronize(c->chunk_ev[1 + (ci & 1)]));
+        if (nchunks > 1) JCB_CUDA(cudaEventSynchronize(c->chunk_ev[1 + (ci & 1)]));
+        else JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1], 0));
         if (ci + 1 < nchunks) JCB_TRY(issue_chunk(ci + 1));
-        if (ci == 0) {
+        if (ci == 0 && !chunked) {
             phase_begin(c, JCB200_T_PIVOT);
-            JCB_TRY(launch_pivot(c, dX, ld, dY, ld, nr, p, q, d_pivot));
+            JCB_TRY(launch_pivot(c, dX, ldX, dY, ldY, nr, p, q, d_pivot));
             phase_end(c, JCB200_T_PIVOT);
         }
-        JCB_TRY(launch_gram(c, dX + r0, ld, dY + r0, ld, dw ? dw + r0 : nullptr, nr, p, q, d_pivot,
+        JCB_TRY(launch_gram(c, dX + r0, ldX, dY + r0, ldY, dw ? dw + r0 : nullptr, nr, p, q, d_pivot,
                             d_packed, ci > 0));
     }
     JCB_TRY(launch_solve(c, d_packed, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxm, dxs, dym, dys,
                          d_sumw));
-    // Scores: into page-locked T the score pass runs in four row blocks, each block's device-to-host copy
-    // (copy stream) under the next block's K5, so the PCIe transfer of T starts a quarter pass after the solve
-    const bool pipeT = nlv > 0 && n >= chunk_min_rows() && is_pinned(T);
-    if (pipeT) {
-        int64_t blk = (n + 3) / 4;
-        blk = (blk + 1) & ~(int64_t)1;
-        int bi = 0;
-        for (int64_t r0 = 0; r0 < n; r0 += blk, ++bi) {
-            const int64_t nr = std::min(blk, n - r0);
-            JCB_TRY(launch_fit_scores(c, dX + r0, ld, nr, p, q, dxm, dxs, dR, nlv, d_pivot, dT + r0, ld));
-            JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (bi & 1)], st));
-            JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[1 + (bi & 1)], 0));
-            if (bi == 0) phase_begin_on(c, JCB200_T_D2H, cs);
-            JCB_TRY(d2h_2d(c, T + r0, ldt, dT + r0, ld, nr, nlv, cs));
+    // Non-finite input (NaN / Inf in X, Y or the weights) shows in the weighted column sums.  The reference
+    // throws from LAPACK's svd at plskern.jl:154 (q > 1) or returns an all-NaN model (q == 1); here the fit
+    // fails with JCB200_ENONFINITE.  plskern! checks BEFORE touching the caller's X and Y.
+    double status = 0.0;
+    if (writeback_xy) {
+        JCB_CUDA(cudaMemcpyAsync(&status, d_sumw + 1, 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaStreamSynchronize(st));
+        if (status != 0.0) {
+            set_error("plskern_fit: X, Y or weights contain NaN or Inf");
+            return JCB200_ENONFINITE;
         }
-        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], cs));
-    } else if (nlv > 0) {
-        JCB_TRY(launch_fit_scores(c, dX, ld, n, p, q, dxm, dxs, dR, nlv, d_pivot, dT, ld));
+    }
+    // ---- scores (and the write-back of plskern!) in row blocks: K5 (and K7) on block b, then its copies to the
+    // host on the copy stream while the next blocks compute — the transfer of T (and of the centred X, Y) starts
+    // a block after the solve.  All kernels are enqueued before any copy (a copy queued ahead of a kernel on
+    // another stream was seen to hold the kernel back).
+    const int nblk = n >= chunk_min_rows() ? (writeback_xy ? 8 : 4) : 1;
+    int64_t blk = (n + nblk - 1) / nblk;
+    blk = (blk + 1) & ~(int64_t)1;
+    int nb_used = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += blk, ++nb_used) {
+        const int64_t nr = std::min(blk, n - r0);
+        if (nlv > 0)
+            JCB_TRY(launch_fit_scores(c, dX + r0, ldX, nr, p, q, dxm, dxs, dR, nlv, d_pivot, dT + r0, ld));
+        if (writeback_xy) {
+            phase_begin(c, JCB200_T_WRITEBACK);
+            JCB_TRY(launch_center_scale(c, dX + r0, ldX, nr, p, dxm, dxs));
+            JCB_TRY(launch_center_scale(c, dY + r0, ldY, nr, q, dym, dys));
+            phase_end(c, JCB200_T_WRITEBACK);
+        }
+        JCB_CUDA(cudaEventRecord(c->blk_ev[nb_used], st));
     }
     JCB_TRY(launch_weights(c, dw, n, d_sumw, dwout));
-    if (writeback_xy) {
-        phase_begin(c, JCB200_T_WRITEBACK);
-        JCB_TRY(launch_center_scale(c, dX, ld, n, p, dxm, dxs));
-        JCB_TRY(launch_center_scale(c, dY, ld, n, q, dym, dys));
-        phase_end(c, JCB200_T_WRITEBACK);
-    }
-
-    if (!pipeT) phase_begin(c, JCB200_T_D2H);
     if (nlv > 0) {
         JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
         JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
@@ -838,18 +997,92 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
     JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
-    if (nlv > 0 && !pipeT) JCB_TRY(d2h_2d(c, T, ldt, dT, ld, n, nlv, st));
+    if (!writeback_xy) JCB_CUDA(cudaMemcpyAsync(&status, d_sumw + 1, 8, cudaMemcpyDeviceToHost, st));
     JCB_TRY(d2h_2d(c, w_out, n, dwout, ld, n, 1, st));
-    if (writeback_xy) {
-        JCB_TRY(d2h_2d(c, X, ldx, dX, ld, n, p, st));
-        JCB_TRY(d2h_2d(c, Y, ldy, dY, ld, n, q, st));
+    {
+        int bi = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += blk, ++bi) {
+            const int64_t nr = std::min(blk, n - r0);
+            JCB_CUDA(cudaStreamWaitEvent(cs, c->blk_ev[bi], 0));
+            if (bi == 0) phase_begin_on(c, JCB200_T_D2H, cs);
+            if (nlv > 0) JCB_TRY(d2h_2d(c, T + r0, ldt, dT + r0, ld, nr, nlv, cs));
+            if (writeback_xy) {
+                JCB_TRY(d2h_2d(c, X + r0, ldx, dX + r0, ldX, nr, p, cs));
+                JCB_TRY(d2h_2d(c, Y + r0, ldy, dY + r0, ldY, nr, q, cs));
+            }
+        }
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], cs));
+        JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));     // the block copies on the copy stream
     }
-    if (pipeT) JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));     // the copies of T on the copy stream
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
+    drain.ok = true;
     phases_collect(c);
+    if (status != 0.0) {
+        set_error("plskern_fit: X, Y or weights contain NaN or Inf");
+        return JCB200_ENONFINITE;
+    }
+    for (int a = 0; a < nlv; ++a) tl_nlv_effective += TT[a] > 0.0;
     return 0;
+}
+
+int jcb200_last_fit_info(int32_t* nlv_effective) {
+    if (nlv_effective) *nlv_effective = tl_nlv_effective;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ resident matrices
+int jcb200_resident_add(const double* A, int64_t lda, int64_t rows, int64_t cols) {
+    API_PROLOGUE();
+    ARG_CHECK(A && rows > 0 && cols > 0 && lda >= rows, "resident_add: bad argument");
+    for (int i = 0; i < c->n_resident; ++i)
+        if (c->resident[i].host == A) {         // registered before: refresh
+            JCB_CUDA(cudaStreamSynchronize(c->stream));
+            resident_drop_at(c, i);
+            break;
+        }
+    if (c->n_resident >= Ctx::MAX_RESIDENT) {
+        set_error("resident_add: at most %d resident matrices", Ctx::MAX_RESIDENT);
+        return JCB200_EINVAL;
+    }
+    const int64_t ld = even_up(rows);
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (size_t)ld * cols * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("resident_add: cudaMalloc of %zu bytes failed: %s", (size_t)ld * cols * 8, cudaGetErrorString(e));
+        return JCB200_ENOMEM;
+    }
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    const int r = h2d_2d(c, d, ld, A, lda, rows, cols, c->stream);
+    phase_end(c, JCB200_T_TOTAL);
+    cudaStreamSynchronize(c->stream);
+    if (r != 0) {
+        cudaFree(d);
+        return r;
+    }
+    phases_collect(c);
+    c->resident[c->n_resident++] = Ctx::Resident{A, lda, rows, cols, d, ld};
+    return 0;
+}
+
+int jcb200_resident_drop(const double* A) {
+    API_PROLOGUE();
+    for (int i = 0; i < c->n_resident; ++i)
+        if (c->resident[i].host == A) {
+            JCB_CUDA(cudaStreamSynchronize(c->stream));
+            resident_drop_at(c, i);
+            return 0;
+        }
+    set_error("resident_drop: matrix is not resident");
+    return JCB200_EINVAL;
+}
+
+int jcb200_resident_count(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    return g_ctx.ready ? g_ctx.n_resident : 0;
 }
 
 // Row-chunk pipeline of the streaming host paths (transform, predict): new rows are independent, so the
@@ -903,7 +1136,7 @@ static int pipeline_rows(Ctx* c, const double* X, int64_t ldx, int64_t m, int64_
     // call is synchronous anyway; the host wait costs the copy engine a few tens of microseconds per chunk.
     auto issue_h2d = [&](int ci) -> int {
         const int64_t r0 = (int64_t)ci * chunk, nr = std::min(chunk, m - r0);
-        JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));
+        if (X) JCB_TRY(h2d_2d(c, dX + r0, ld, X + r0, ldx, nr, p, cs));     // X == nullptr: resident on the device
         mark(cs);
         if (ci == nch - 1) phase_end_on(c, JCB200_T_H2D, cs);
         JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
@@ -956,11 +1189,15 @@ int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const d
               "transform: bad argument");
     if (nlv == 0) return 0;
     ARG_CHECK(R && T_out && ldt >= m, "transform: NULL R or output");
-    const int64_t ld = even_up(m);
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    const Ctx::Resident* rx = resident_find(c, X, ldx, m, p);
+    const int64_t ld = rx ? rx->ld : even_up(m);
+    if (!rx) {
+        JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+        invalidate_cv(c);
+    }
     JCB_TRY(ensure(c->hT, (size_t)ld * nlv * 8));
     JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + (size_t)p * nlv + 16) * 8));
-    double* dX = (double*)c->hX.p;
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
     double* dT = (double*)c->hT.p;
     Carver cv(c->hSmall.p);
     double* dxm = cv.take(p);
@@ -973,7 +1210,7 @@ int jcb200_transform(const double* X, int64_t ldx, int64_t m, int64_t p, const d
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * nlv * 8, cudaMemcpyHostToDevice, st));
     JCB_TRY(pipeline_rows(
-        c, X, ldx, m, p, dX, ld, pipeline_chunk(m),
+        c, rx ? nullptr : X, ldx, m, p, dX, ld, pipeline_chunk(m),
         [&](int, int64_t r0, int64_t nr, int) {
             return launch_xmul(c, dX + r0, ld, nr, p, dxm, dxs, dR, p, nlv, nullptr, dT + r0, ld);
         },
@@ -992,14 +1229,15 @@ int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double
     ARG_CHECK(X && xmeans && xscales && out && m > 0 && p > 0 && nlv >= 0 && ldx >= m && ldo >= m,
               "xfit: bad argument");
     ARG_CHECK(nlv == 0 || (R && P), "xfit: NULL R or P");
-    const int64_t ld = even_up(m);
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    const Ctx::Resident* rx = resident_find(c, X, ldx, m, p);
+    const int64_t ld = rx ? rx->ld : even_up(m);
+    if (!rx) JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
     JCB_TRY(ensure(c->hT, (size_t)ld * std::max<int>(nlv, 1) * 8));
     const int64_t chunk = pipeline_chunk(m), cmax = even_up(std::min(chunk, m));
     JCB_TRY(ensure(c->hPred, (size_t)2 * cmax * p * 8));           // two chunk-local result slots (ld = cmax)
     JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + 2 * (size_t)p * nlv + 16) * 8));
-    c->cv_hostX = c->cv_hostY = nullptr;
-    double* dX = (double*)c->hX.p;
+    invalidate_cv(c);
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
     double* dT = (double*)c->hT.p;
     double* dOut = (double*)c->hPred.p;
     Carver cv(c->hSmall.p);
@@ -1018,7 +1256,7 @@ int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double
     }
     // m x p in and m x p out: the two directions of the link overlap chunk by chunk
     JCB_TRY(pipeline_rows(
-        c, X, ldx, m, p, dX, ld, chunk,
+        c, rx ? nullptr : X, ldx, m, p, dX, ld, chunk,
         [&](int, int64_t r0, int64_t nr, int slot) {
             if (nlv > 0) JCB_TRY(launch_xmul(c, dX + r0, ld, nr, p, dxm, dxs, dR, p, nlv, nullptr, dT + r0, ld));
             return launch_xfit(c, dX + r0, ld, dOut + (size_t)slot * cmax * p, cmax, nr, p, dT + r0, ld, dP, p,
@@ -1030,6 +1268,12 @@ int jcb200_xfit(const double* X, int64_t ldx, int64_t m, int64_t p, const double
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);
+    // the bang forms overwrite their argument on the host: a resident copy of it is stale now
+    for (int i = 0; i < c->n_resident; ++i)
+        if (c->resident[i].host == (const void*)out) {
+            resident_drop_at(c, i);
+            break;
+        }
     return 0;
 }
 
@@ -1078,14 +1322,18 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     ARG_CHECK(a == 0 || (R && C), "predict_sweep: NULL model");
     const int nk = k_hi - k_lo + 1;
     for (int i = 0; i < nk; ++i) ARG_CHECK(pred_out[i], "predict_sweep: NULL output matrix");
-    const int64_t ld = even_up(m);
+    const Ctx::Resident* rx = resident_find(c, X, ldx, m, p);
+    const int64_t ld = rx ? rx->ld : even_up(m);
     const int64_t chunk = pipeline_chunk(m);
     const int64_t cmax = std::min(chunk, m);             // rows of the largest chunk
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    if (!rx) {
+        JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+        invalidate_cv(c);
+    }
     JCB_TRY(ensure(c->hPred, (size_t)2 * nk * cmax * q * 8));      // two chunk-local result slots
     const size_t nd = (size_t)p * a + (size_t)q * a + 2 * (p + q) + (size_t)p * q + q + 64;
     JCB_TRY(ensure(c->hSmall, nd * 8));
-    double* dX = (double*)c->hX.p;
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
     double* dPred = (double*)c->hPred.p;
     Carver cv(c->hSmall.p);
     double* dR = cv.take((size_t)p * a);
@@ -1112,7 +1360,7 @@ int jcb200_predict_sweep(const double* X, int64_t ldx, int64_t m, int64_t p, int
     if (single) JCB_TRY(launch_coef(c, dR, dC, dxm, dxs, dym, dys, p, q, k_lo, dB, dint));
     // the results of a chunk are nk chunk-local nr x q matrices (ld = nr) in its slot of dPred
     JCB_TRY(pipeline_rows(
-        c, X, ldx, m, p, dX, ld, chunk,
+        c, rx ? nullptr : X, ldx, m, p, dX, ld, chunk,
         [&](int, int64_t r0, int64_t nr, int slot) {
             double* dP = dPred + (size_t)slot * nk * cmax * q;
             if (single) return launch_xmul(c, dX + r0, ld, nr, p, dxm, nullptr, dB, p, (int)q, dym, dP, nr);
@@ -1141,16 +1389,20 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
               "gridscore: bad argument");
     ARG_CHECK(a == 0 || (R && C), "gridscore: NULL model");
     const int ka = k_hi > 0 ? k_hi : 1;
+    const Ctx::Resident* rx = resident_find(c, X, ldx, m, p);
+    const Ctx::Resident* ry = resident_find(c, Y, ldy, m, q);
     const int64_t ld = even_up(m);
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    if (!rx) JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    if (!ry) JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    if (!rx || !ry) invalidate_cv(c);
     JCB_TRY(ensure(c->hT, (size_t)ld * ka * 8));
     JCB_TRY(ensure(c->hPred, (size_t)ld * 2 * q * 8));
     const int64_t plen = packed_len(ka, 2 * q);
     const size_t nd = (size_t)p * a + (size_t)q * a + 2 * (p + q) + plen + (ka + 2 * q + 1) + 64;
     JCB_TRY(ensure(c->hSmall, nd * 8));
-    double* dX = (double*)c->hX.p;
-    double* dY = (double*)c->hY.p;
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
+    double* dY = ry ? ry->dev : (double*)c->hY.p;
+    const int64_t ldX = rx ? rx->ld : ld, ldY = ry ? ry->ld : ld;
     double* dT = (double*)c->hT.p;
     double* dYaug = (double*)c->hPred.p;
     Carver cv(c->hSmall.p);
@@ -1166,8 +1418,8 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
     phases_reset(c);
     phase_begin(c, JCB200_T_TOTAL);
     phase_begin(c, JCB200_T_H2D);
-    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, m, p, st));
-    JCB_TRY(h2d_2d(c, dY, ld, Y, ldy, m, q, st));
+    if (!rx) JCB_TRY(h2d_2d(c, dX, ldX, X, ldx, m, p, st));
+    if (!ry) JCB_TRY(h2d_2d(c, dY, ldY, Y, ldy, m, q, st));
     if (a > 0) {
         JCB_CUDA(cudaMemcpyAsync(dR, R, (size_t)p * a * 8, cudaMemcpyHostToDevice, st));
         JCB_CUDA(cudaMemcpyAsync(dC, C, (size_t)q * a * 8, cudaMemcpyHostToDevice, st));
@@ -1178,11 +1430,11 @@ int jcb200_gridscore(const double* X, int64_t ldx, const double* Y, int64_t ldy,
     JCB_CUDA(cudaMemcpyAsync(dys, yscales, q * 8, cudaMemcpyHostToDevice, st));
     phase_end(c, JCB200_T_H2D);
     if (k_hi > 0) {
-        JCB_TRY(launch_xmul(c, dX, ld, m, p, dxm, dxs, dR, p, k_hi, nullptr, dT, ld));
+        JCB_TRY(launch_xmul(c, dX, ldX, m, p, dxm, dxs, dR, p, k_hi, nullptr, dT, ld));
     } else {
         JCB_CUDA(cudaMemsetAsync(dT, 0, (size_t)ld * 8, st));
     }
-    JCB_TRY(launch_gridscore_gram(c, dY, ld, dT, ld, dC, dys, dym, m, (int)q, k_hi, ka, dYaug, ld, dpv, dpk));
+    JCB_TRY(launch_gridscore_gram(c, dY, ldY, dT, ld, dC, dys, dym, m, (int)q, k_hi, ka, dYaug, ld, dpv, dpk));
     std::vector<double> hpk((size_t)plen);
     JCB_CUDA(cudaMemcpyAsync(hpk.data(), dpk, (size_t)plen * 8, cudaMemcpyDeviceToHost, st));
     phase_end(c, JCB200_T_TOTAL);
@@ -1199,12 +1451,16 @@ int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const dou
     ARG_CHECK(X && xmeans && xscales && weights && n > 0 && p > 0 && ldx >= n && a >= 0,
               "summary: bad argument");
     ARG_CHECK(a == 0 || (P && TT && xvar && pvar && cumpvar), "summary: NULL model or output");
-    const int64_t ld = even_up(n);
+    const Ctx::Resident* rx = resident_find(c, X, ldx, n, p);
+    const int64_t ld = rx ? rx->ld : even_up(n);
     const int gx = 32;
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
+    if (!rx) {
+        JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+        invalidate_cv(c);
+    }
+    JCB_TRY(ensure(c->hW, (size_t)even_up(n) * 2 * 8));
     JCB_TRY(ensure(c->hSmall, (size_t)(2 * p + (size_t)gx * p + 16) * 8));
-    double* dX = (double*)c->hX.p;
+    double* dX = rx ? rx->dev : (double*)c->hX.p;
     double* dw = (double*)c->hW.p;
     Carver cv(c->hSmall.p);
     double* dxm = cv.take(p);
@@ -1212,14 +1468,18 @@ int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const dou
     double* dpart = cv.take((size_t)gx * p);
     double* dout = cv.take(2);
     cudaStream_t st = c->stream;
-    JCB_TRY(h2d_2d(c, dX, ld, X, ldx, n, p, st));
-    JCB_TRY(h2d_2d(c, dw, ld, weights, n, n, 1, st));
+    phases_reset(c);
+    phase_begin(c, JCB200_T_TOTAL);
+    if (!rx) JCB_TRY(h2d_2d(c, dX, ld, X, ldx, n, p, st));
+    JCB_TRY(h2d_2d(c, dw, even_up(n), weights, n, n, 1, st));
     JCB_CUDA(cudaMemcpyAsync(dxm, xmeans, p * 8, cudaMemcpyHostToDevice, st));
     JCB_CUDA(cudaMemcpyAsync(dxs, xscales, p * 8, cudaMemcpyHostToDevice, st));
     JCB_TRY(launch_sstot(c, dX, ld, n, p, dxm, dxs, dw, dpart, gx, dout));
     double sstot = 0.0;
     JCB_CUDA(cudaMemcpyAsync(&sstot, dout, 8, cudaMemcpyDeviceToHost, st));
+    phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
+    phases_collect(c);
     // tt_adj[l] = (p_l' p_l) tt_l ; pvar = tt_adj / sstot ; xvar = tt_adj / n      (plskern.jl:253-258)
     double cum = 0.0;
     for (int l = 0; l < a; ++l) {
@@ -1284,10 +1544,15 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
 
     // ---- device copies of X, Y (kept across calls for the repetitions of one CV)
     const int64_t ld = even_up(n);
-    const bool have = reuse_xy && c->cv_hostX == X && c->cv_hostY == Y && c->cv_n == n && c->cv_p == p &&
-                      c->cv_q == q;
-    JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    const Ctx::Resident* rx = resident_find(c, X, ldx, n, p);
+    const Ctx::Resident* ry = resident_find(c, Y, ldy, n, q);
+    const bool res = rx && ry;          // both registered with jcb200_resident_add: no copy at all
+    const bool have = res || (reuse_xy && c->cv_hostX == X && c->cv_hostY == Y && c->cv_n == n && c->cv_p == p &&
+                              c->cv_q == q);
+    if (!res) {
+        JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+        JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    }
     JCB_TRY(ensure(c->cvX, (size_t)ldp * p * 8));
     JCB_TRY(ensure(c->cvY, (size_t)ldp * q * 8));
     JCB_TRY(ensure(c->cvIdx, (size_t)ldp * 8));
@@ -1298,8 +1563,8 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
     const size_t small = (size_t)(p + q + 1) + 3 * (size_t)p * ka + (size_t)q * ka + ka + 2 * (p + q) + 2 +
                          (ka + 2 * q + 1) + 64;
     JCB_TRY(ensure(c->hSmall, small * 8));
-    double* dX = (double*)c->hX.p;
-    double* dY = (double*)c->hY.p;
+    double* dX = res ? rx->dev : (double*)c->hX.p;
+    double* dY = res ? ry->dev : (double*)c->hY.p;
     double* dXp = (double*)c->cvX.p;
     double* dYp = (double*)c->cvY.p;
     int64_t* dIdx = (int64_t*)c->cvIdx.p;

@@ -1,0 +1,290 @@
+// Peer-memory exchange of the row-sharded fit, one process per GPU.
+//
+// The path has ONE exchange: the sum of the packed partial Grams [Gxx | Gxy | gyy | sx | sy | sw] (2 MB at C2,
+// 32 MB at C4), preceded by the pivot of rank 0 (p + q + 1 doubles).  Both go straight through peer HBM over
+// NVLink / NVSwitch, mapped into every process with CUDA IPC — no collective library, no host round trip:
+//
+//   push   every rank copies its packed block, coalesced 16-byte stores, into slot [rank] of EVERY rank's window
+//          (its own included); the last block to finish raises flag [rank] in every window (release, system
+//          scope, after a system fence: the data has landed before the flag can be seen)
+//   sum    the next kernel on the stream waits until all `world` flags of its own window carry this exchange's
+//          sequence number (acquire, system scope) and adds the slots in rank order: local HBM reads only, the
+//          same order on every rank, so every rank holds the same bits (K3/K4 then run redundantly and agree)
+//
+// Windows are double-buffered by the parity of the sequence number: a rank can only reach exchange k+2 after
+// every peer has pushed k+1, which each peer does (stream order) after it has finished reading exchange k.
+// The pivot uses the same scheme with rank 0 as the only writer.
+#include <algorithm>
+#include <cstring>
+
+#include "jcb_internal.cuh"
+
+namespace jcb {
+
+constexpr int COMM_MAX = 8;
+constexpr int64_t COMM_PIVOT_CAP = 16384;           // doubles per pivot buffer (p + q + 1 <= 16384)
+constexpr size_t COMM_HDR_BYTES = 4096;
+constexpr int COMM_FLAG_STRIDE = 16;                // uint64 per flag: one 128-byte line each
+
+struct CommHeader {                                  // lives at the start of every window
+    unsigned long long flag_packed[COMM_MAX * COMM_FLAG_STRIDE];   // [r * 16]: rank r's block of exchange `seq` landed
+    unsigned long long flag_pivot[COMM_FLAG_STRIDE];               // rank 0's pivot of fit `seq` landed
+    unsigned int done;                                             // blocks of the running push that have finished
+};
+static_assert(sizeof(CommHeader) <= COMM_HDR_BYTES, "header");
+
+struct Comm {
+    bool ready = false, connected = false;
+    int rank = 0, world = 1;
+    int64_t cap = 0;                 // doubles per slot
+    unsigned char* win = nullptr;    // own window
+    unsigned char* peer[COMM_MAX] = {};   // every rank's window in this process's address space
+    unsigned long long seq_packed = 0, seq_pivot = 0;
+    unsigned char** d_peer = nullptr;     // device copy of peer[]
+};
+static Comm g_comm;
+
+static inline size_t comm_window_bytes(int world, int64_t cap) {
+    return COMM_HDR_BYTES + 2 * (size_t)COMM_PIVOT_CAP * 8 + 2 * (size_t)world * (size_t)cap * 8;
+}
+__host__ __device__ static inline double* win_pivot(unsigned char* w, int parity) {
+    return (double*)(w + COMM_HDR_BYTES) + (size_t)parity * COMM_PIVOT_CAP;
+}
+__host__ __device__ static inline double* win_slot(unsigned char* w, int parity, int world, int64_t cap, int r) {
+    return (double*)(w + COMM_HDR_BYTES + 2 * (size_t)COMM_PIVOT_CAP * 8) + ((size_t)parity * world + r) * (size_t)cap;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// push: packed block -> slot [rank] of every window, then flag [rank] everywhere (last block)
+__global__ void __launch_bounds__(256)
+comm_push_kernel(const double* __restrict__ src, int64_t len, unsigned char* const* __restrict__ peers, int rank,
+                 int world, int64_t cap, int parity, unsigned long long seq) {
+    double* dst[COMM_MAX];
+#pragma unroll
+    for (int r = 0; r < COMM_MAX; ++r) dst[r] = r < world ? win_slot(peers[r], parity, world, cap, rank) : nullptr;
+    const int64_t n2 = len >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 v = reinterpret_cast<const double2*>(src)[i];
+#pragma unroll
+        for (int r = 0; r < COMM_MAX; ++r)
+            if (r < world) reinterpret_cast<double2*>(dst[r])[i] = v;
+    }
+    if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double v = src[len - 1];
+        for (int r = 0; r < world; ++r) dst[r][len - 1] = v;
+    }
+    __threadfence_system();          // this thread's remote stores are performed before anything that follows
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CommHeader* own = reinterpret_cast<CommHeader*>(peers[rank]);
+        const unsigned int prev = atomicAdd(&own->done, 1u);
+        if (prev == gridDim.x - 1) {          // every block has fenced its stores
+            own->done = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r)
+                st_release_sys(&reinterpret_cast<CommHeader*>(peers[r])->flag_packed[rank * COMM_FLAG_STRIDE], seq);
+        }
+    }
+}
+
+// sum: wait for the `world` flags of this exchange, then out = sum over ranks of slot[r] (rank order)
+__global__ void __launch_bounds__(256)
+comm_sum_kernel(double* __restrict__ out, int64_t len, unsigned char* win, int world, int64_t cap, int parity,
+                unsigned long long seq) {
+    const CommHeader* hdr = reinterpret_cast<const CommHeader*>(win);
+    if (threadIdx.x < world) {
+        const unsigned long long* f = &hdr->flag_packed[threadIdx.x * COMM_FLAG_STRIDE];
+        while (ld_acquire_sys(f) < seq) __nanosleep(40);
+    }
+    __syncthreads();
+    const double* s0 = win_slot(win, parity, world, cap, 0);
+    const int64_t n2 = len >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 v[COMM_MAX];
+#pragma unroll
+        for (int r = 0; r < COMM_MAX; ++r)
+            if (r < world) v[r] = __ldcg(reinterpret_cast<const double2*>(s0 + (size_t)r * cap) + i);
+        double2 s = v[0];
+#pragma unroll
+        for (int r = 1; r < COMM_MAX; ++r)
+            if (r < world) {
+                s.x += v[r].x;
+                s.y += v[r].y;
+            }
+        reinterpret_cast<double2*>(out)[i] = s;
+    }
+    if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += __ldcg(s0 + (size_t)r * cap + len - 1);
+        out[len - 1] = s;
+    }
+}
+
+// rank 0: pivot -> every peer's pivot buffer, then the pivot flag there
+__global__ void __launch_bounds__(256)
+comm_pivot_publish_kernel(const double* __restrict__ pivot, int npv, unsigned char* const* __restrict__ peers,
+                          int world, int parity, unsigned long long seq) {
+    for (int r = 1; r < world; ++r) {
+        double* dst = win_pivot(peers[r], parity);
+        for (int i = threadIdx.x; i < npv; i += blockDim.x) dst[i] = pivot[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int r = 1; r < world; ++r)
+            st_release_sys(&reinterpret_cast<CommHeader*>(peers[r])->flag_pivot[0], seq);
+}
+
+// rank > 0: wait for rank 0's pivot of this fit, copy it out of the own window
+__global__ void __launch_bounds__(256)
+comm_pivot_fetch_kernel(double* __restrict__ pivot, int npv, unsigned char* win, int parity, unsigned long long seq) {
+    const CommHeader* hdr = reinterpret_cast<const CommHeader*>(win);
+    if (threadIdx.x == 0)
+        while (ld_acquire_sys(&hdr->flag_pivot[0]) < seq) __nanosleep(40);
+    __syncthreads();
+    const double* src = win_pivot(win, parity);
+    for (int i = threadIdx.x; i < npv; i += blockDim.x) pivot[i] = __ldcg(src + i);
+}
+
+void comm_destroy_locked() {
+    Comm& m = g_comm;
+    if (!m.ready) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < m.world; ++r)
+        if (r != m.rank && m.peer[r]) cudaIpcCloseMemHandle(m.peer[r]);
+    if (m.d_peer) cudaFree(m.d_peer);
+    if (m.win) cudaFree(m.win);
+    m = Comm();
+}
+
+int comm_create_locked(Ctx* c, int rank, int world, int64_t max_packed_len, void* handle_out) {
+    Comm& m = g_comm;
+    if (m.ready) {
+        set_error("comm_create: a communicator exists; call jcb200_comm_destroy first");
+        return JCB200_EINVAL;
+    }
+    if (world < 1 || world > COMM_MAX || rank < 0 || rank >= world || max_packed_len < 1 || !handle_out) {
+        set_error("comm_create: need 1 <= world <= %d, 0 <= rank < world, max_packed_len > 0", COMM_MAX);
+        return JCB200_EINVAL;
+    }
+    m.rank = rank;
+    m.world = world;
+    m.cap = (max_packed_len + 1) & ~(int64_t)1;
+    const size_t bytes = comm_window_bytes(world, m.cap);
+    cudaError_t e = cudaMalloc(&m.win, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("comm_create: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        m = Comm();
+        return JCB200_ENOMEM;
+    }
+    JCB_CUDA(cudaMemset(m.win, 0, COMM_HDR_BYTES));
+    JCB_CUDA(cudaMalloc(&m.d_peer, COMM_MAX * sizeof(unsigned char*)));
+    JCB_CUDA(cudaDeviceSynchronize());
+    memset(handle_out, 0, JCB200_IPC_HANDLE_BYTES);
+    if (world > 1) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) <= JCB200_IPC_HANDLE_BYTES, "IPC handle size");
+        JCB_CUDA(cudaIpcGetMemHandle(&h, m.win));
+        memcpy(handle_out, &h, sizeof(h));
+    }
+    m.peer[rank] = m.win;
+    m.ready = true;
+    m.connected = world == 1;
+    if (m.connected) JCB_CUDA(cudaMemcpy(m.d_peer, m.peer, sizeof(m.peer), cudaMemcpyHostToDevice));
+    (void)c;
+    return 0;
+}
+
+int comm_connect_locked(const void* all_handles) {
+    Comm& m = g_comm;
+    if (!m.ready || !all_handles) {
+        set_error("comm_connect: call jcb200_comm_create first");
+        return JCB200_EINVAL;
+    }
+    if (m.connected) return 0;
+    for (int r = 0; r < m.world; ++r) {
+        if (r == m.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)all_handles + (size_t)r * JCB200_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("comm_connect: cudaIpcOpenMemHandle of rank %d's window failed: %s", r, cudaGetErrorString(e));
+            return (int)e;
+        }
+        m.peer[r] = (unsigned char*)ptr;
+    }
+    JCB_CUDA(cudaMemcpy(m.d_peer, m.peer, sizeof(m.peer), cudaMemcpyHostToDevice));
+    m.connected = true;
+    return 0;
+}
+
+int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,
+               int64_t q, double* d_pivot) {
+    Comm& m = g_comm;
+    if (!m.ready || !m.connected) {
+        set_error("comm_pivot: no connected communicator");
+        return JCB200_EINVAL;
+    }
+    const int npv = (int)(p + q + 1);
+    if (npv > COMM_PIVOT_CAP) {
+        set_error("comm_pivot: p + q + 1 = %d exceeds %lld", npv, (long long)COMM_PIVOT_CAP);
+        return JCB200_EINVAL;
+    }
+    const unsigned long long seq = ++m.seq_pivot;
+    const int parity = (int)(seq & 1);
+    if (m.rank == 0) {
+        JCB_TRY(launch_pivot(c, dX, ldx, dY, ldy, n, p, q, d_pivot));
+        if (m.world > 1) {
+            comm_pivot_publish_kernel<<<1, 256, 0, c->stream>>>(d_pivot, npv, m.d_peer, m.world, parity, seq);
+            JCB_LAUNCH_CHECK();
+        }
+    } else {
+        comm_pivot_fetch_kernel<<<1, 256, 0, c->stream>>>(d_pivot, npv, m.win, parity, seq);
+        JCB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int comm_allreduce(Ctx* c, double* d_packed, int64_t len) {
+    Comm& m = g_comm;
+    if (!m.ready || !m.connected) {
+        set_error("comm_allreduce: no connected communicator");
+        return JCB200_EINVAL;
+    }
+    if (len < 1 || len > m.cap) {
+        set_error("comm_allreduce: length %lld exceeds the window capacity %lld", (long long)len, (long long)m.cap);
+        return JCB200_EINVAL;
+    }
+    if (((uintptr_t)d_packed & 15) != 0) {
+        set_error("comm_allreduce: buffer must be 16-byte aligned");
+        return JCB200_EALIGN;
+    }
+    if (m.world == 1) return 0;
+    const unsigned long long seq = ++m.seq_packed;
+    const int parity = (int)(seq & 1);
+    // enough blocks to keep the NVLink write queues full, few enough that the completion counter is cheap
+    const int grid = (int)std::min<int64_t>(((len >> 1) + 255) / 256, 4 * (int64_t)c->num_sms);
+    phase_begin(c, JCB200_T_REDUCE);
+    comm_push_kernel<<<grid > 0 ? grid : 1, 256, 0, c->stream>>>(d_packed, len, m.d_peer, m.rank, m.world, m.cap,
+                                                                parity, seq);
+    JCB_LAUNCH_CHECK();
+    comm_sum_kernel<<<grid > 0 ? grid : 1, 256, 0, c->stream>>>(d_packed, len, m.win, m.world, m.cap, parity, seq);
+    JCB_LAUNCH_CHECK();
+    phase_end(c, JCB200_T_REDUCE);
+    return 0;
+}
+
+}  // namespace jcb

@@ -69,6 +69,9 @@ struct Ctx {
     size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf pivot_ws;
+    Buf pivot_sample;               // device copy of the host row sample the streamed fit takes its pivot from
+    void* pivot_host = nullptr;     // page-locked staging of that sample
+    size_t pivot_host_bytes = 0;
     Buf locw_ws;
     Buf solve_ws;
     Buf xmul_ws;
@@ -88,10 +91,24 @@ struct Ctx {
     void* stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2];
     cudaEvent_t chunk_ev[3];
-    // timing
-    cudaEvent_t ev_begin[JCB200_NPHASE], ev_end[JCB200_NPHASE];
-    bool ev_used[JCB200_NPHASE];
+    cudaEvent_t blk_ev[8];               // host fit: row block b scored (and centred in place)
+    // timing: a phase may occur several times in one call (row chunks, score blocks); every occurrence has
+    // its own event pair and the reported time is their SUM (kernel time, not the span under the copies)
+    static constexpr int PHASE_SLOTS = 24;
+    cudaEvent_t ev_begin[JCB200_NPHASE][PHASE_SLOTS], ev_end[JCB200_NPHASE][PHASE_SLOTS];
+    int ev_cnt[JCB200_NPHASE];        // completed occurrences
+    bool ev_open[JCB200_NPHASE];      // begin recorded, end pending
     double last_ms[JCB200_NPHASE];
+    // resident matrices (jcb200_resident_add): host arrays whose device copy is kept across calls
+    struct Resident {
+        const void* host;
+        int64_t ld_host, rows, cols;
+        double* dev;
+        int64_t ld;
+    };
+    static constexpr int MAX_RESIDENT = 16;
+    Resident resident[MAX_RESIDENT];
+    int n_resident = 0;
 };
 
 Ctx* ctx();                               // the process-wide context (API mutex must be held)
@@ -153,6 +170,14 @@ int launch_packed_sub(Ctx* c, const double* a, const double* b, double* out, int
 int launch_packed_add(Ctx* c, double* acc, const double* b, int64_t len, int first);
 void gridscore_from_packed(const double* pk, int ka, int q, int k_lo, int k_hi, const double* C,
                            const double* ys, double* ssr, double* sumres, double* ysum, double* ysumsq);
+
+// peer-memory exchange (comm.cu); the API mutex must be held
+int comm_create_locked(Ctx* c, int rank, int world, int64_t max_packed_len, void* handle_out);
+int comm_connect_locked(const void* all_handles);
+void comm_destroy_locked();
+int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,
+               int64_t q, double* d_pivot);
+int comm_allreduce(Ctx* c, double* d_packed, int64_t len);
 
 inline int64_t packed_len(int64_t p, int64_t q) { return p * p + p * q + q + p + q + 1; }
 // offsets into the packed buffer

@@ -31,7 +31,10 @@ constexpr int LV_THREADS = 512;
 constexpr int LV_CLUSTER = 8;
 
 // ----------------------------------------------------------------------------------------- K3
-// stats: delta, means, scales (one block)
+// stats: delta, means, scales (ONE block), and the non-finite check: a NaN or Inf anywhere in X, Y or the
+// weights reaches the weighted column sums (or their total), so testing p + q + 1 numbers covers the input.
+// sumw[0] = S, sumw[1] = 0 (finite) / 1 (non-finite input: the LV loop is skipped, the host entry points fail
+// with JCB200_ENONFINITE — the reference throws from svd at plskern.jl:154).
 __global__ void finalize_stats_kernel(const double* __restrict__ packed,
                                       const double* __restrict__ pivot, int p, int q, int scal,
                                       double* __restrict__ xmeans, double* __restrict__ xscales,
@@ -43,9 +46,10 @@ __global__ void finalize_stats_kernel(const double* __restrict__ packed,
     const double* sx = gyy + Q;
     const double* sy = sx + P;
     const double S = sy[Q];
-    if (threadIdx.x == 0 && blockIdx.x == 0) *sumw = S;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p + q; j += gridDim.x * blockDim.x) {
+    int bad = !isfinite(S);
+    for (int j = threadIdx.x; j < p + q; j += blockDim.x) {
         if (j < p) {
+            bad |= !isfinite(sx[j]);
             const double d = sx[j] / S;
             delta[j] = d;
             xmeans[j] = pivot[j] + d;
@@ -53,11 +57,17 @@ __global__ void finalize_stats_kernel(const double* __restrict__ packed,
             xscales[j] = scal ? sqrt((gxx[j + (int64_t)j * P] - pivot[j] * sx[j]) / S - d * d) : 1.0;
         } else {
             const int k = j - p;
+            bad |= !isfinite(sy[k]);
             const double d = sy[k] / S;
             delta[j] = d;
             ymeans[k] = pivot[j] + d;
             yscales[k] = scal ? sqrt((gyy[k] - pivot[j] * sy[k]) / S - d * d) : 1.0;
         }
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        sumw[0] = S;
+        sumw[1] = bad ? 1.0 : 0.0;
     }
 }
 
@@ -114,6 +124,7 @@ struct LvParams {
     double* C;
     double* TT;
     int p, q, nlv;
+    const double* status; // K3's non-finite flag (sumw[1]): non-zero = skip the loop (all CTAs alike)
     int xty_smem;        // XtY resident in shared memory (every CTA deflates its own full copy)
     double* Ppriv;       // LV_CLUSTER private copies of P and R (p x nlv each): with XtY in smem a CTA
     double* Rpriv;       // reads back only what it wrote itself, so one cluster barrier per LV suffices
@@ -196,6 +207,7 @@ __device__ __forceinline__ double warp_dot_ss(const double* __restrict__ a,
 
 __global__ void __cluster_dims__(LV_CLUSTER, 1, 1) __launch_bounds__(LV_THREADS, 1)
 lvloop_kernel(const LvParams prm) {
+    if (prm.status[0] != 0.0) return;          // non-finite input: every CTA leaves before the first barrier
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ double sm[];
     const int p = prm.p, q = prm.q, nlv = prm.nlv;
@@ -239,8 +251,16 @@ lvloop_kernel(const LvParams prm) {
                 w_s[k] = x;
                 s += x * x;
             }
-            const double nrm = sqrt(block_sum(s, red));
-            for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+            // XtY == 0 (constant y, or more LVs than the data carry): the reference divides 0/0 here
+            // (plskern.jl:152); like the q > 1 branch (svd of a zero matrix: U = I) take w = e_1, the LV is
+            // then inert (tt = 0 -> c = 0, P = 0) and predictions stay finite
+            const double nrm2 = block_sum(s, red);
+            if (nrm2 > 0.0) {
+                const double nrm = sqrt(nrm2);
+                for (int k = tid; k < p; k += LV_THREADS) w_s[k] /= nrm;
+            } else {
+                for (int k = tid; k < p; k += LV_THREADS) w_s[k] = (k == 0) ? 1.0 : 0.0;
+            }
         } else {
             // M = XtY' XtY (symmetric q x q): a warp takes up to 4 (i <= j) pairs per pass so that their
             // loads and reductions overlap
@@ -576,6 +596,7 @@ __device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t 
 
 template <bool GS>
 __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams prm) {
+    if (prm.status[0] != 0.0) return;          // non-finite input: every CTA leaves before the first barrier
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(8) uint64_t bars[5];          // A, B, C, D, B2 (the rare w = e_1 redo)
@@ -930,7 +951,7 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
     double* Rpriv = Ppriv + (size_t)LV_CLUSTER * p * nlv;
 
     phase_begin(c, JCB200_T_FINALIZE);
-    finalize_stats_kernel<<<(int)((p + q + 255) / 256), 256, 0, c->stream>>>(
+    finalize_stats_kernel<<<1, 512, 0, c->stream>>>(
         d_packed, d_pivot, (int)p, (int)q, scal, dxmeans, dxscales, dymeans, dyscales, dsumw, delta);
     JCB_LAUNCH_CHECK();
     dim3 grid((unsigned)((p + 127) / 128), (unsigned)(p + q));
@@ -952,6 +973,7 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
     prm.p = (int)p;
     prm.q = (int)q;
     prm.nlv = nlv;
+    prm.status = dsumw + 1;
     prm.Ppriv = Ppriv;
     prm.Rpriv = Rpriv;
 #ifdef JCB_K1_TRACE

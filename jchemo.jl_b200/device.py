@@ -108,6 +108,16 @@ def gram_dev(X, Y, w, n, pivot, packed, accumulate=False):
                "gram_dev")
 
 
+def comm_pivot_dev(X, Y, n, pivot):
+    """Pivot of rank 0's rows, published to every rank through the peer windows (jcb200_comm_pivot_dev)."""
+    _lib.check(_lib.lib().jcb200_comm_pivot_dev(_p(X), _ld(X), _p(Y), _ld(Y), n, X.shape[0], Y.shape[0],
+                                                _p(pivot)), "comm_pivot_dev")
+
+
+def comm_allreduce_dev(packed):
+    _lib.check(_lib.lib().jcb200_comm_allreduce_dev(_p(packed), packed.numel()), "comm_allreduce_dev")
+
+
 def solve_dev(packed, pivot, model, scal=False):
     _lib.check(_lib.lib().jcb200_solve_dev(
         _p(packed), _p(pivot), model.p, model.q, model.nlv, int(scal), _p(model.P), _p(model.R),

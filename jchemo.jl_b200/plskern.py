@@ -122,6 +122,60 @@ def _fit(X, Y, weights, nlv, scal, writeback):
     return Plsr(T, P, R, W, Cm, TT, xmeans, xscales, ymeans, yscales, w_out, None)
 
 
+def last_fit_info():
+    """Facts about the calling thread's last fit: `nlv_effective` = LVs that carry information (TT > 0);
+    degenerate LVs (the reference divides 0/0 at plskern.jl:152,166) are returned inert."""
+    k = C.c_int32(0)
+    _lib.check(_lib.lib().jcb200_last_fit_info(C.byref(k)), "last_fit_info")
+    return namedtuple("FitInfo", ["nlv_effective"])(k.value)
+
+
+def _resident_mat(A):
+    if not (isinstance(A, np.ndarray) and A.ndim == 2 and A.dtype == np.float64 and A.flags.f_contiguous):
+        raise TypeError("resident: needs a Float64 column-major matrix (the very array later calls are handed)")
+    return A
+
+
+def resident_add(A):
+    """Upload A once and keep the device copy (jcb200_resident_add): later calls that are handed this very array
+    as X or Y skip the host-to-device transfer.  Do not modify A on the host while it is resident."""
+    A = _resident_mat(A)
+    _lib.check(_lib.lib().jcb200_resident_add(_ptr(A), _ld(A), A.shape[0], A.shape[1]), "resident_add")
+    return A
+
+
+def resident_drop(A):
+    _lib.check(_lib.lib().jcb200_resident_drop(_ptr(_resident_mat(A))), "resident_drop")
+
+
+class resident:
+    """`with resident(X, Y): fm = plskern(X, Y, nlv=25); summary(fm, X); gridscorelv(...)` — one upload for the
+    block (the reference's workflows reuse one X: gridscore.jl:179-180, plskern.jl:246-249)."""
+
+    def __init__(self, *mats):
+        self.mats = [_resident_mat(A) for A in mats]
+
+    def __enter__(self):
+        done = []
+        try:
+            for A in self.mats:
+                resident_add(A)
+                done.append(A)
+        except Exception:
+            for A in done:
+                resident_drop(A)
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        for A in self.mats:
+            try:
+                resident_drop(A)
+            except _lib.JchemoB200Error:
+                pass                      # dropped by a call that overwrote it on the host (xfit!, xresid!)
+        return False
+
+
 def plskern(X, Y, weights=None, *, nlv, scal=False):
     """plskern(X, Y, weights = ones(n); nlv, scal = false) — inputs are left untouched (:106-110)."""
     return _fit(_fmat(X), _fmat(Y), weights, nlv, scal, writeback=False)

@@ -5,8 +5,9 @@ The only exchange of the path is one sum all-reduce of the packed partial-Gram b
 After it every rank holds bit-identical inputs, runs K3/K4 redundantly and computes the scores of
 its own rows; predict/transform shard by rows with no communication.
 
-`reduce_packed` is the whole host-side protocol and is backend-agnostic (NCCL on GPUs, gloo in the
-CPU tests).
+Two carriers for that exchange: `PeerComm` — the library's own kernels over CUDA-IPC peer windows
+(NVLink, no collective call, no host synchronisation; the B200 path) — and torch.distributed
+(`broadcast_pivot` / `reduce_packed`: NCCL on GPUs, gloo in the CPU tests of the host-side protocol).
 """
 import torch
 import torch.distributed as dist
@@ -50,7 +51,7 @@ def shard_rows(n, rank, world):
 
 def broadcast_pivot(pivot, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.broadcast(pivot, src=0, group=group)
+        dist.broadcast(pivot, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     return pivot
 
 
@@ -61,21 +62,72 @@ def reduce_packed(packed, group=None):
     return packed
 
 
-def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None):
-    """X [p, ld], Y [q, ld], w [n_local] or None hold this rank's rows on its GPU."""
+class PeerComm:
+    """The exchange of the sharded fit through peer HBM (jcb200_comm_*, csrc/comm.cu) instead of a collective
+    library: every rank pushes its packed block into slot [rank] of every rank's CUDA-IPC window over NVLink and
+    the next kernel on each rank adds the slots in rank order once the `world` flags are up.  No host
+    synchronisation and no NCCL call inside the fit; torch.distributed only carries the 64-byte IPC handles
+    once, here.  Every rank must construct it (collective) and issue the same sequence of fits."""
+
+    def __init__(self, max_packed_len, group=None):
+        import ctypes as C
+        from . import _lib
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        _lib.check(_lib.lib().jcb200_comm_create(self.rank, self.world, int(max_packed_len), handle), "comm_create")
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(handle), group=group)
+            blob = b"".join(gathered)
+            assert len(blob) == self.world * _lib.IPC_HANDLE_BYTES
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            _lib.check(_lib.lib().jcb200_comm_connect(buf), "comm_connect")
+            dist.barrier(group=group)        # every window is mapped before the first push
+
+    def pivot(self, X, Y, n_local, pivot):
+        dev.comm_pivot_dev(X, Y, max(n_local, 1), pivot)
+
+    def allreduce(self, packed):
+        dev.comm_allreduce_dev(packed)
+
+    def close(self):
+        from . import _lib
+        _lib.check(_lib.lib().jcb200_comm_destroy(), "comm_destroy")
+
+
+def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None, comm=None):
+    """X [p, ld], Y [q, ld], w [n_local] or None hold this rank's rows on its GPU.  The library's kernels and
+    the collectives must share one stream: the fit is issued on torch's CURRENT stream (the library is switched
+    to it here).  `comm`: a PeerComm (peer-HBM exchange) — else torch.distributed (NCCL / gloo) carries the
+    pivot broadcast and the packed all-reduce.  A rank may hold no rows (n_local == 0): it contributes zeros and
+    still takes part in the exchange."""
+    dev.use_current_stream()
     p, q = X.shape[0], Y.shape[0]
     if pivot is None:
         pivot = torch.empty(p + q + 1, dtype=torch.float64, device=X.device)
     if packed is None:
         packed = torch.empty(dev.packed_len(p, q), dtype=torch.float64, device=X.device)
-    dev.pivot_dev(X, Y, n_local, pivot)
-    broadcast_pivot(pivot, group)
-    dev.gram_dev(X, Y, w, n_local, pivot, packed)
-    reduce_packed(packed, group)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if comm is not None:
+        comm.pivot(X, Y, n_local, pivot)            # rank 0 computes and publishes, the others fetch
+    else:
+        if rank == 0:
+            dev.pivot_dev(X, Y, n_local, pivot)
+        broadcast_pivot(pivot, group)
+    if n_local > 0:
+        dev.gram_dev(X, Y, w, n_local, pivot, packed)
+    else:
+        packed.zero_()
+    if comm is not None:
+        comm.allreduce(packed)
+    else:
+        reduce_packed(packed, group)
     dev.solve_dev(packed, pivot, model, scal)
-    if model.nlv > 0:
-        dev.scores_dev(X, n_local, model, pivot=pivot)
-    dev.weights_dev(w, n_local, model)
+    if n_local > 0:
+        if model.nlv > 0:
+            dev.scores_dev(X, n_local, model, pivot=pivot)
+        dev.weights_dev(w, n_local, model)
     return model
 
 
@@ -107,19 +159,23 @@ def _side_stream(device):
 
 
 def fit_sharded_from_host(hX, hY, hw, X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None,
-                          hT=None):
+                          hT=None, comm=None):
     """fit_sharded with this rank's rows in page-locked HOST tensors hX [p, n_local], hY [q, n_local]
     (hw [n_local] or None); X, Y, w are the device buffers they are streamed into.  The rows go over in
     chunks on a side stream and K1 runs on chunk i while chunk i+1 is in flight, the partial Grams
-    accumulating in `packed`; the pivot comes from rank 0's first chunk.  The host paces the pipeline — the
+    accumulating in `packed`; the pivot comes from rank 0's first chunk.  Issued on torch's CURRENT stream (the
+    library is switched to it here).  The host paces the pipeline — the
     copy of chunk i+1 is issued after the kernel on chunk i — because a copy queued ahead of a kernel was
     observed to hold the kernel back.  With hT [nlv, n_local] (page-locked) the scores are
     copied back in four row blocks, each under the next block's K5."""
+    dev.use_current_stream()
     p, q = X.shape[0], Y.shape[0]
     if pivot is None:
         pivot = torch.empty(p + q + 1, dtype=torch.float64, device=X.device)
     if packed is None:
         packed = torch.empty(dev.packed_len(p, q), dtype=torch.float64, device=X.device)
+    if n_local <= 0:
+        raise ValueError("fit_sharded_from_host: this rank holds no rows (use fit_sharded, which accepts empty shards)")
     main, side = torch.cuda.current_stream(X.device), _side_stream(X.device)
     b = chunk_bounds(n_local)
     side.wait_stream(main)
@@ -141,13 +197,19 @@ def fit_sharded_from_host(hX, hY, hw, X, Y, w, n_local, model, scal=False, group
         ev.synchronize()
         Xc, Yc = X[:, r0:r1], Y[:, r0:r1]
         if ci == 0:
-            dev.pivot_dev(Xc, Yc, r1 - r0, pivot)
-            broadcast_pivot(pivot, group)
+            if comm is not None:
+                comm.pivot(Xc, Yc, r1 - r0, pivot)
+            else:
+                dev.pivot_dev(Xc, Yc, r1 - r0, pivot)
+                broadcast_pivot(pivot, group)
         dev.gram_dev(Xc, Yc, None if w is None or hw is None else w[r0:r1], r1 - r0, pivot, packed,
                      accumulate=ci > 0)
         if ci + 2 < len(b):
             ev = issue(ci + 1)
-    reduce_packed(packed, group)
+    if comm is not None:
+        comm.allreduce(packed)
+    else:
+        reduce_packed(packed, group)
     dev.solve_dev(packed, pivot, model, scal)
     if model.nlv > 0:
         if hT is None or n_local < 400000:

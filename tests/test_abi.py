@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_packed_len(lib):
-    assert lib.jcb200_version() == 100
+    assert lib.jcb200_version() == 200
     p, q = 500, 10
     assert lib.jcb200_packed_len(p, q) == p * p + p * q + 2 * q + p + 1
 
