@@ -284,6 +284,10 @@ int jcb200_fill_uniform_dev(double* d, int64_t ld, int64_t n_rows, int64_t n_col
 int jcb200_comm_create(int32_t rank, int32_t world, int64_t max_packed_len, void* handle_out);
 int jcb200_comm_connect(const void* all_handles);
 int jcb200_comm_destroy(void);
+/* Waits that were given up since jcb200_comm_create (a peer never arrived within ~4 s: it died or issued a
+ * different sequence of calls).  A waiter that gives up poisons its result with NaN, so the fit then fails with
+ * JCB200_ENONFINITE instead of hanging the GPU.  Synchronises the library stream. */
+int jcb200_comm_timeouts(void);
 /* Rank 0 computes the pivot of ITS rows (jcb200_pivot_dev) and publishes it; the other ranks fetch it out of
  * rank 0's window.  d_pivot (p + q + 1 doubles) is valid on every rank afterwards (stream order). */
 int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "jcb200_comm_create": (C.c_int, [i32, i32, i64, C.c_void_p]),
     "jcb200_comm_connect": (C.c_int, [C.c_void_p]),
     "jcb200_comm_destroy": (C.c_int, []),
+    "jcb200_comm_timeouts": (C.c_int, []),
     "jcb200_comm_pivot_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
     "jcb200_comm_allreduce_dev": (C.c_int, [C.c_void_p, i64]),
     "jcb200_plskern_fit": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32,

@@ -229,10 +229,11 @@ static thread_local int32_t tl_nlv_effective = 0;
 // digits (delta^2 / sigma^2 of them).  Costs ~4 MB of transfer at C2.
 static int host_sample_pivot(Ctx* c, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t n,
                              int64_t p, int64_t q, double* d_pivot, cudaStream_t cs) {
-    const int nblk = 16;
-    int64_t brow = 64;
+    const int nblk = (int)std::min<int64_t>(16, n);
+    const int64_t stride = n / nblk;
+    int64_t brow = std::min<int64_t>(64, stride);
     while (brow > 2 && (size_t)nblk * brow * (p + q) * 8 > ((size_t)24 << 20)) brow >>= 1;
-    const int64_t ns = nblk * brow, stride = n / nblk;
+    const int64_t ns = nblk * brow;
     const size_t bytes = (size_t)ns * (p + q) * 8;
     if (c->pivot_host_bytes < bytes) {
         if (c->pivot_host) cudaFreeHost(c->pivot_host);
@@ -719,6 +720,12 @@ int jcb200_comm_destroy(void) {
     API_PROLOGUE();
     comm_destroy_locked();
     return 0;
+}
+
+int jcb200_comm_timeouts(void) {
+    API_PROLOGUE();
+    JCB_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_timeouts_locked();
 }
 
 int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,

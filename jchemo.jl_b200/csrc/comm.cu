@@ -15,6 +15,7 @@
 // every peer has pushed k+1, which each peer does (stream order) after it has finished reading exchange k.
 // The pivot uses the same scheme with rank 0 as the only writer.
 #include <algorithm>
+#include <cstddef>
 #include <cstring>
 
 #include "jcb_internal.cuh"
@@ -30,7 +31,11 @@ struct CommHeader {                                  // lives at the start of ev
     unsigned long long flag_packed[COMM_MAX * COMM_FLAG_STRIDE];   // [r * 16]: rank r's block of exchange `seq` landed
     unsigned long long flag_pivot[COMM_FLAG_STRIDE];               // rank 0's pivot of fit `seq` landed
     unsigned int done;                                             // blocks of the running push that have finished
+    unsigned int timeouts;                                         // waits given up (a peer never arrived)
 };
+// A wait that never ends would hang the GPU: after ~4 s (a peer has died or left the sequence) the waiter gives
+// up, counts it in the header and poisons its result with NaN, which K3's non-finite check turns into an error.
+constexpr long long COMM_WAIT_CYCLES = 8000000000ll;
 static_assert(sizeof(CommHeader) <= COMM_HDR_BYTES, "header");
 
 struct Comm {
@@ -100,12 +105,27 @@ comm_push_kernel(const double* __restrict__ src, int64_t len, unsigned char* con
 __global__ void __launch_bounds__(256)
 comm_sum_kernel(double* __restrict__ out, int64_t len, unsigned char* win, int world, int64_t cap, int parity,
                 unsigned long long seq) {
-    const CommHeader* hdr = reinterpret_cast<const CommHeader*>(win);
+    CommHeader* hdr = reinterpret_cast<CommHeader*>(win);
+    int late = 0;
     if (threadIdx.x < world) {
         const unsigned long long* f = &hdr->flag_packed[threadIdx.x * COMM_FLAG_STRIDE];
-        while (ld_acquire_sys(f) < seq) __nanosleep(40);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            __nanosleep(40);
+            if (clock64() - t0 > COMM_WAIT_CYCLES) {
+                late = 1;
+                break;
+            }
+        }
     }
-    __syncthreads();
+    late = __syncthreads_or(late);
+    if (late) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            atomicAdd(&hdr->timeouts, 1u);
+            out[len - 1] = __longlong_as_double(0x7ff8000000000000ll);     // sum(w) = NaN: K3 flags the fit
+        }
+        return;
+    }
     const double* s0 = win_slot(win, parity, world, cap, 0);
     const int64_t n2 = len >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -148,12 +168,23 @@ comm_pivot_publish_kernel(const double* __restrict__ pivot, int npv, unsigned ch
 // rank > 0: wait for rank 0's pivot of this fit, copy it out of the own window
 __global__ void __launch_bounds__(256)
 comm_pivot_fetch_kernel(double* __restrict__ pivot, int npv, unsigned char* win, int parity, unsigned long long seq) {
-    const CommHeader* hdr = reinterpret_cast<const CommHeader*>(win);
-    if (threadIdx.x == 0)
-        while (ld_acquire_sys(&hdr->flag_pivot[0]) < seq) __nanosleep(40);
-    __syncthreads();
+    CommHeader* hdr = reinterpret_cast<CommHeader*>(win);
+    int late = 0;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&hdr->flag_pivot[0]) < seq) {
+            __nanosleep(40);
+            if (clock64() - t0 > COMM_WAIT_CYCLES) {
+                late = 1;
+                atomicAdd(&hdr->timeouts, 1u);
+                break;
+            }
+        }
+    }
+    late = __syncthreads_or(late);
     const double* src = win_pivot(win, parity);
-    for (int i = threadIdx.x; i < npv; i += blockDim.x) pivot[i] = __ldcg(src + i);
+    for (int i = threadIdx.x; i < npv; i += blockDim.x)
+        pivot[i] = late ? __longlong_as_double(0x7ff8000000000000ll) : __ldcg(src + i);
 }
 
 void comm_destroy_locked() {
@@ -229,6 +260,14 @@ int comm_connect_locked(const void* all_handles) {
     JCB_CUDA(cudaMemcpy(m.d_peer, m.peer, sizeof(m.peer), cudaMemcpyHostToDevice));
     m.connected = true;
     return 0;
+}
+
+int comm_timeouts_locked() {
+    Comm& m = g_comm;
+    if (!m.ready) return 0;
+    unsigned int t = 0;
+    cudaMemcpy(&t, m.win + offsetof(CommHeader, timeouts), sizeof(t), cudaMemcpyDeviceToHost);
+    return (int)t;
 }
 
 int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,

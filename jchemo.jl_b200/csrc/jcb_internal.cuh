@@ -175,6 +175,7 @@ void gridscore_from_packed(const double* pk, int ka, int q, int k_lo, int k_hi, 
 int comm_create_locked(Ctx* c, int rank, int world, int64_t max_packed_len, void* handle_out);
 int comm_connect_locked(const void* all_handles);
 void comm_destroy_locked();
+int comm_timeouts_locked();
 int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,
                int64_t q, double* d_pivot);
 int comm_allreduce(Ctx* c, double* d_packed, int64_t len);
