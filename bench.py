@@ -675,20 +675,30 @@ def e2e_leg(np, torch, dist, jc, dev, sharded, rank, world, device, gloo, comm, 
         hX.copy_(torch.from_numpy(Xp.T))          # restore the raw inputs
         hY.copy_(torch.from_numpy(Yp.T))
         if ndev == 1:
-            # device-resident data handle: fit + summary + gridscore on ONE upload of X
+            # device-resident data handle: fit + summary + gridscore on ONE upload of X (second pass timed: the
+            # first one pays one-off costs — pandas import, workspace growth, K1 schedules of the new shapes)
+            def workflow():
+                t0 = time.perf_counter()
+                fm = jc.plskern(Xh, Yh, nlv=NLV)
+                t1 = time.perf_counter()
+                jc.summary(fm, Xh)
+                t2 = time.perf_counter()
+                jc.gridscorelv(Xh, Yh, Xh, Yh, score="rmsep", nlv=range(0, NLV + 1))
+                t3 = time.perf_counter()
+                return t1 - t0, t2 - t1, t3 - t2
+            workflow()
+            plain = workflow()                     # every call uploads X again
             t0 = time.perf_counter()
             with jc.resident(Xh, Yh):
-                t1 = time.perf_counter()
-                fm = jc.plskern(Xh, Yh, nlv=NLV)
-                t2 = time.perf_counter()
-                jc.summary(fm, Xh)
-                t3 = time.perf_counter()
-                jc.gridscorelv(Xh, Yh, Xh, Yh, score="rmsep", nlv=range(0, NLV + 1))
-                t4 = time.perf_counter()
-            out["resident"] = {"upload_seconds": t1 - t0, "fit_seconds": t2 - t1, "summary_seconds": t3 - t2,
-                               "gridscorelv_seconds": t4 - t3,
-                               "how": "jcb200_resident_add(X), (Y) once; plskern, summary, gridscorelv(fit + 26-nlv "
-                                      "sweep) then run without any transfer of X"}
+                up = time.perf_counter() - t0
+                workflow()
+                res = workflow()
+            out["resident"] = {"upload_seconds": up, "fit_seconds": res[0], "summary_seconds": res[1],
+                               "gridscorelv_seconds": res[2],
+                               "same_calls_without_handle_seconds": {"fit": plain[0], "summary": plain[1],
+                                                                     "gridscorelv": plain[2]},
+                               "how": "jcb200_resident_add(X), (Y) once; plskern, summary, gridscorelv (a fit + the "
+                                      "26-nlv scoring sweep) then run without any transfer of X"}
         del Xp, Yp
     out["_Xh"], out["_Yh"] = Xh, Yh
     return out
