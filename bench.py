@@ -306,7 +306,8 @@ def main():
     if world > 1:
         try:
             comm = sharded.PeerComm(dev.packed_len(C4["p"], C4["q"]))
-            comm_note = "peer HBM windows over CUDA IPC (csrc/comm.cu): push to every rank's slot + flag, ordered sum"
+            comm_note = ("peer HBM windows over CUDA IPC (csrc/comm.cu), fused: K1b stores the reduced block into every "
+                         "rank's slot and raises the flags, K3 reads the ordered sum of the slots")
         except Exception as ex:                     # IPC not permitted on this box: say so, use NCCL
             comm, comm_note = None, f"NCCL all-reduce (peer windows unavailable: {ex})"
         ok = torch.tensor([1.0 if comm is not None else 0.0], **f64)
@@ -358,15 +359,17 @@ def main():
     exchange = {"used": comm_note}
     if world > 1 and extras:
         # the same step with the other carrier, and the two exchanges alone on the C2 buffer
-        other = None if use_comm is not None else comm
-
-        def step_other():
-            sharded.fit_sharded(X, Y, None, n_loc, model, scal=False, pivot=pivot, packed=packed, comm=other)
-        if use_comm is not None or comm is not None:
+        def variant(cm, fused):
+            def f():
+                sharded.fit_sharded(X, Y, None, n_loc, model, scal=False, pivot=pivot, packed=packed, comm=cm,
+                                    fused=fused)
             for _ in range(2):
-                step_other()
-            exchange["step_ms_other_carrier"] = {"carrier": "nccl" if other is None else "peer",
-                                                 "ms_per_step": timed(step_other, max(4, K // 2))}
+                f()
+            return timed(f, max(4, K // 2))
+        exchange["step_ms"] = {"nccl_allreduce": variant(None, False)}
+        if comm is not None:
+            exchange["step_ms"]["peer_push_and_sum_kernels"] = variant(comm, False)
+            exchange["step_ms"]["peer_fused_into_K1b_K3"] = variant(comm, True)
         buf = torch.zeros(dev.packed_len(P, Q), **f64)
         if comm is not None:
             for _ in range(3):

@@ -22,7 +22,7 @@ def rel(x, y):
     return float((x - y).norm() / y.norm())
 
 
-def case(n, p, q, nlv, weighted, scal, reps=1):
+def case(n, p, q, nlv, weighted, scal, reps=1, fused=True):
     lo, hi = sharded.shard_rows(n, rank, world)
     nl = hi - lo
     X = dev.colmajor_empty(max(nl, 2), p); Y = dev.colmajor_empty(max(nl, 2), q)
@@ -36,7 +36,7 @@ def case(n, p, q, nlv, weighted, scal, reps=1):
         w = (w + 0.5).reshape(-1)
     m = dev.DeviceModel(max(nl, 2), p, q, nlv)
     for _ in range(reps):                      # several exchanges back to back: the double-buffered windows
-        sharded.fit_sharded(X, Y, w, nl, m, scal=scal, comm=comm)
+        sharded.fit_sharded(X, Y, w, nl, m, scal=scal, comm=comm, fused=fused)
     torch.cuda.synchronize()
     errs = {}
     if comm is not None:
@@ -67,7 +67,7 @@ def case(n, p, q, nlv, weighted, scal, reps=1):
                      "B": rel((m.R.T / m.xscales[:, None]) @ m.C, (m1.R.T / m1.xscales[:, None]) @ m1.C),
                      "T_shard": rel(m.T[:nlv, :nl] * s[:, None], m1.T[:nlv, :nl]),
                      "weights_shard": rel(m.weights[:nl], m1.weights[:nl])})
-        print(f"sharded ({world} GPUs, {a.comm}) n={n} p={p} q={q} vs single GPU:", errs, flush=True)
+        print(f"sharded ({world} GPUs, {a.comm}, fused={fused}) n={n} p={p} q={q} vs single GPU:", errs, flush=True)
     ok = all(v < 1e-10 for v in errs.values())
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -77,6 +77,10 @@ def case(n, p, q, nlv, weighted, scal, reps=1):
 ok = case(400_000, 500, 10, 25, True, True, reps=3)
 ok &= case(30_001, 37, 3, 6, False, False, reps=4)
 ok &= case(2, 3, 1, 1, False, False)            # rank 1 (and up) hold no rows
+if comm is not None:                            # the unfused form (push + sum kernels) and a mix of both
+    ok &= case(30_001, 37, 3, 6, True, True, reps=3, fused=False)
+    ok &= case(100_000, 130, 2, 9, False, False, reps=2, fused=True)
+    ok &= case(2, 3, 1, 1, False, False, fused=False)
 if comm is not None:
     ok &= jc.lib().jcb200_comm_timeouts() == 0
     comm.close()

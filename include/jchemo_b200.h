@@ -292,8 +292,19 @@ int jcb200_comm_timeouts(void);
  * rank 0's window.  d_pivot (p + q + 1 doubles) is valid on every rank afterwards (stream order). */
 int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                           int64_t p, int64_t q, double* d_pivot);
-/* d_packed (len doubles) <- sum over ranks of d_packed, in place, same bits on every rank. */
+/* d_packed (len doubles) <- sum over ranks of d_packed, in place, same bits on every rank (push kernel + sum
+ * kernel; used when the partial Gram was accumulated over row chunks). */
 int jcb200_comm_allreduce_dev(double* d_packed, int64_t len);
+/* The FUSED form for device-resident shards — the exchange has no kernel of its own:
+ *   jcb200_comm_gram_dev   K1 on this rank's n rows (n == 0: the rank contributes zeros), then K1b writes the reduced
+ *                          block straight into slot [rank] of every rank's window over NVLink and raises the flags;
+ *   jcb200_comm_solve_dev  K3 waits for the `world` flags, reads the packed Gram as the sum of the slots in rank
+ *                          order, then K4 — arguments as jcb200_solve_dev without d_packed. */
+int jcb200_comm_gram_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw, int64_t n,
+                         int64_t p, int64_t q, const double* d_pivot);
+int jcb200_comm_solve_dev(const double* d_pivot, int64_t p, int64_t q, int32_t nlv, int32_t scal, double* dP,
+                          double* dR, double* dW, double* dC, double* dTT, double* dxmeans, double* dxscales,
+                          double* dymeans, double* dyscales, double* dsumw);
 
 /* Whole single-GPU fit on device-resident inputs (pivot, gram, solve, scores [, write-back]);
  * dT n*nlv (ld = ldt), dw_out n.  Used by bench.py for the HBM-resident `value`. */

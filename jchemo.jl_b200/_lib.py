@@ -39,6 +39,8 @@ SIGNATURES = {
     "jcb200_comm_timeouts": (C.c_int, []),
     "jcb200_comm_pivot_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, i64, i64, i64, C.c_void_p]),
     "jcb200_comm_allreduce_dev": (C.c_int, [C.c_void_p, i64]),
+    "jcb200_comm_gram_dev": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, C.c_void_p]),
+    "jcb200_comm_solve_dev": (C.c_int, [C.c_void_p, i64, i64, i32, i32] + [C.c_void_p] * 10),
     "jcb200_plskern_fit": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, i64, i64, i32,
                                      i32, i32, C.c_void_p, i64] + [C.c_void_p] * 10 +
                            [C.POINTER(i32)]),

@@ -735,6 +735,25 @@ int jcb200_comm_pivot_dev(const double* dX, int64_t ldx, const double* dY, int64
     return comm_pivot(c, dX, ldx, dY, ldy, n, p, q, d_pivot);
 }
 
+int jcb200_comm_gram_dev(const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw, int64_t n,
+                         int64_t p, int64_t q, const double* d_pivot) {
+    API_PROLOGUE();
+    ARG_CHECK(d_pivot && n >= 0 && p > 0 && q > 0, "comm_gram_dev: bad argument");
+    ARG_CHECK(n == 0 || (dX && dY && ldx >= n && ldy >= n), "comm_gram_dev: bad argument");
+    phases_reset(c);
+    return comm_gram(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot);
+}
+
+int jcb200_comm_solve_dev(const double* d_pivot, int64_t p, int64_t q, int32_t nlv, int32_t scal, double* dP,
+                          double* dR, double* dW, double* dC, double* dTT, double* dxmeans, double* dxscales,
+                          double* dymeans, double* dyscales, double* dsumw) {
+    API_PROLOGUE();
+    ARG_CHECK(d_pivot && p > 0 && q > 0 && nlv >= 0 && dxmeans && dxscales && dymeans && dyscales && dsumw,
+              "comm_solve_dev: bad argument");
+    ARG_CHECK(nlv == 0 || (dP && dR && dW && dC && dTT), "comm_solve_dev: NULL output");
+    return comm_solve(c, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans, dxscales, dymeans, dyscales, dsumw);
+}
+
 int jcb200_comm_allreduce_dev(double* d_packed, int64_t len) {
     API_PROLOGUE();
     ARG_CHECK(d_packed && len > 0, "comm_allreduce_dev: bad argument");

@@ -297,6 +297,68 @@ int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t 
     return 0;
 }
 
+// Fused exchange of the sharded fit: K1b writes this rank's reduced block straight into slot [rank] of every
+// window (its own included) and raises the flags; comm_solve then runs K3 on the SUM of the slots.  No kernel of
+// the exchange's own, no extra pass over the block.
+int comm_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw, int64_t n,
+              int64_t p, int64_t q, const double* d_pivot) {
+    Comm& m = g_comm;
+    if (!m.ready || !m.connected) {
+        set_error("comm_gram: no connected communicator");
+        return JCB200_EINVAL;
+    }
+    const int64_t len = packed_len(p, q);
+    if (len > m.cap) {
+        set_error("comm_gram: packed length %lld exceeds the window capacity %lld", (long long)len, (long long)m.cap);
+        return JCB200_EINVAL;
+    }
+    const unsigned long long seq = ++m.seq_packed;
+    const int parity = (int)(seq & 1);
+    if (n <= 0) {
+        // a rank without rows contributes zeros: push them from a zeroed scratch block
+        JCB_TRY(ensure(c->pivot_sample, (size_t)len * 8 + 16));
+        double* z = (double*)c->pivot_sample.p;
+        JCB_CUDA(cudaMemsetAsync(z, 0, (size_t)len * 8, c->stream));
+        const int grid = (int)std::min<int64_t>(((len >> 1) + 255) / 256, 4 * (int64_t)c->num_sms);
+        comm_push_kernel<<<grid > 0 ? grid : 1, 256, 0, c->stream>>>(z, len, m.d_peer, m.rank, m.world, m.cap, parity, seq);
+        JCB_LAUNCH_CHECK();
+        return 0;
+    }
+    ReduceDst dst;
+    dst.n = m.world;
+    for (int r = 0; r < m.world; ++r) {
+        // own window first: K1b's accumulate-free stores go to dst.p[*] alike, order is irrelevant
+        dst.p[r] = win_slot(m.peer[r], parity, m.world, m.cap, m.rank);
+        dst.flag[r] = &reinterpret_cast<CommHeader*>(m.peer[r])->flag_packed[m.rank * COMM_FLAG_STRIDE];
+    }
+    dst.done = &reinterpret_cast<CommHeader*>(m.win)->done;
+    dst.seq = seq;
+    return launch_gram_to(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot, dst, 0);
+}
+
+int comm_solve(Ctx* c, const double* d_pivot, int64_t p, int64_t q, int nlv, int scal, double* dP, double* dR,
+               double* dW, double* dC, double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+               double* dyscales, double* dsumw) {
+    Comm& m = g_comm;
+    if (!m.ready || !m.connected || m.seq_packed == 0) {
+        set_error("comm_solve: no exchange in flight (call jcb200_comm_gram_dev first)");
+        return JCB200_EINVAL;
+    }
+    const unsigned long long seq = m.seq_packed;
+    const int parity = (int)(seq & 1);
+    PackedSrc src;
+    src.base = win_slot(m.win, parity, m.world, m.cap, 0);
+    src.stride = m.cap;
+    src.n = m.world;
+    CommHeader* hdr = reinterpret_cast<CommHeader*>(m.win);
+    src.flags = hdr->flag_packed;
+    src.flag_stride = COMM_FLAG_STRIDE;
+    src.seq = seq;
+    src.timeouts = &hdr->timeouts;
+    return launch_solve_src(c, src, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans, dxscales, dymeans,
+                            dyscales, dsumw);
+}
+
 int comm_allreduce(Ctx* c, double* d_packed, int64_t len) {
     Comm& m = g_comm;
     if (!m.ready || !m.connected) {

@@ -127,16 +127,44 @@ int pinned_free(void* p);
 void pinned_release_all();
 void phase_end(Ctx* c, int ph);
 
+// Where K1b writes the reduced Gram block: one buffer (the fit's own packed buffer), or — row-sharded fit, fused
+// exchange — slot [rank] of EVERY rank's peer window, after which the last block raises flag [rank] in every window.
+struct ReduceDst {
+    int n = 1;                                 // destinations
+    double* p[8] = {};
+    unsigned int* done = nullptr;              // completion counter of the launch (own window); null: no signalling
+    unsigned long long* flag[8] = {};          // flag [rank] of every window
+    unsigned long long seq = 0;
+};
+// Where K3 reads the packed Gram: one buffer, or the sum over the `n` slots of the own peer window (rank order:
+// the same bits on every rank), after waiting for the `n` flags of this exchange.
+struct PackedSrc {
+    const double* base = nullptr;
+    int64_t stride = 0;
+    int n = 1;
+    const unsigned long long* flags = nullptr; // n flags, `flag_stride` apart; null: nothing to wait for
+    int flag_stride = 16;
+    unsigned long long seq = 0;
+    unsigned int* timeouts = nullptr;          // counts waits that were given up
+};
+
 // ---------------------------------------------------------------- kernel launchers
 int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                  int64_t p, int64_t q, double* d_pivot);
 int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
                 const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
                 double* d_packed, int accumulate);
+int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
+                   const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
+                   const ReduceDst& dst, int accumulate);
 int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t p, int64_t q,
                  int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
                  double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
                  double* dsumw);
+int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_t p, int64_t q,
+                     int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
+                     double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
+                     double* dsumw);
 int launch_xmul(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t p, const double* dmu,
                 const double* dsigma, const double* dM, int64_t ldm, int ncol, const double* dbias,
                 double* dOut, int64_t ldo);
@@ -179,6 +207,11 @@ int comm_timeouts_locked();
 int comm_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n, int64_t p,
                int64_t q, double* d_pivot);
 int comm_allreduce(Ctx* c, double* d_packed, int64_t len);
+int comm_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, const double* dw, int64_t n,
+              int64_t p, int64_t q, const double* d_pivot);
+int comm_solve(Ctx* c, const double* d_pivot, int64_t p, int64_t q, int nlv, int scal, double* dP, double* dR,
+               double* dW, double* dC, double* dTT, double* dxmeans, double* dxscales, double* dymeans,
+               double* dyscales, double* dsumw);
 
 inline int64_t packed_len(int64_t p, int64_t q) { return p * p + p * q + q + p + q + 1; }
 // offsets into the packed buffer

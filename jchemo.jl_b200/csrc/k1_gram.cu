@@ -473,70 +473,103 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     }
 }
 
-// K1b — ordered split-K reduce of the partial units into the packed buffer
-// [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw].  One block per (group, warp-unit).
+// K1b — ordered split-K reduce of the partial units into the packed layout
+// [Gxx p*p | Gxy p*q | gyy q | sx p | sy q | sw].  One block per (group, warp-unit): the 32x32 unit is summed over
+// its segments in fragment order (fixed order: deterministic), transposed through shared memory and written as
+// 32 columns of 32 consecutive doubles (256-byte runs) to EVERY destination — the fit's own packed buffer, or, in
+// the row-sharded fit, slot [rank] of every rank's peer window over NVLink: the exchange needs no copy of its own.
+// The last block to finish (system fence + completion counter) raises this rank's flag in every window.
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restrict__ group_seg,
-                   const double* __restrict__ partials, double* __restrict__ packed, int p, int q,
+                   const double* __restrict__ partials, const ReduceDst dst, int p, int q,
                    int nbx, int accumulate) {
+    __shared__ double tile[32 * 33];
     const int gi = blockIdx.x / NCW, wu = blockIdx.x % NCW;
     const GroupDesc* gd = &groups[gi];
     const UnitDesc u = gd->unit[wu];
-    if (!u.kind) return;
-    const int sbeg = group_seg[gi], send = group_seg[gi + 1];
-    const int ba = gd->blk[u.sa], bb = gd->blk[u.sb];
-    const bool ay = ba >= nbx, by = bb >= nbx;
-    const int rowbase = (ay ? ba - nbx : ba) * CB, colbase = (by ? bb - nbx : bb) * CB;
-    const int64_t P = p, Q = q;
-    double* gxx = packed;
-    double* gxy = packed + P * P;
-    double* gyy = gxy + P * Q;
-    double* sx = gyy + Q;
-    double* sy = sx + P;
-    double* sw = sy + Q;
-    const int nelem = 1024 + (u.kind == 2 ? 32 : 0);
-    for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
-        // fixed summation order (deterministic), but eight loads in flight: one dependent load per segment made
-        // this kernel a chain of memory latencies (38 us for 22 MB)
-        double s = 0.0;
-        const double* src = partials + (int64_t)wu * UNIT_STRIDE + e;
-        int sg = sbeg;
-        for (; sg + 8 <= send; sg += 8) {
-            double v[8];
+    if (u.kind) {
+        const int sbeg = group_seg[gi], send = group_seg[gi + 1];
+        const int ba = gd->blk[u.sa], bb = gd->blk[u.sb];
+        const bool ay = ba >= nbx, by = bb >= nbx;
+        const int rowbase = (ay ? ba - nbx : ba) * CB, colbase = (by ? bb - nbx : bb) * CB;
+        const int64_t P = p, Q = q;
+        const int64_t o_gxy = P * P, o_gyy = o_gxy + P * Q, o_sx = o_gyy + Q, o_sy = o_sx + P, o_sw = o_sy + Q;
+        const int nelem = 1024 + (u.kind == 2 ? 32 : 0);
+        for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+            // fixed summation order (deterministic), but eight loads in flight: one dependent load per segment made
+            // this kernel a chain of memory latencies (38 us for 22 MB)
+            double s = 0.0;
+            const double* src = partials + (int64_t)wu * UNIT_STRIDE + e;
+            int sg = sbeg;
+            for (; sg + 8 <= send; sg += 8) {
+                double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + (int64_t)(sg + k) * NCW * UNIT_STRIDE);
+                for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + (int64_t)(sg + k) * NCW * UNIT_STRIDE);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s += v[k];
-        }
-        for (; sg < send; ++sg) s += __ldcs(src + (int64_t)sg * NCW * UNIT_STRIDE);
-        double* dst = nullptr;
-        if (e < 1024) {
-            const int blk = e >> 6, ln = (e >> 1) & 31, half = e & 1;
-            const int mb = blk >> 2, nb = blk & 3;
-            if (u.kind == 2 && mb > nb) continue;
-            const int row = rowbase + mb * 8 + (ln >> 2), col = colbase + nb * 8 + (ln & 3) * 2 + half;
-            if (!ay && !by) {
-                if (row < p && col < p) dst = gxx + row + (int64_t)col * P;
-            } else if (!ay && by) {
-                if (row < p && col < q) dst = gxy + row + (int64_t)col * P;
-            } else if (ay && by) {
-                if (row == col && row < q) dst = gyy + row;
+                for (int k = 0; k < 8; ++k) s += v[k];
             }
-        } else {
-            const int col = colbase + (e - 1024);
-            if (!by) {
-                if (col < p) dst = sx + col;
+            for (; sg < send; ++sg) s += __ldcs(src + (int64_t)sg * NCW * UNIT_STRIDE);
+            if (e < 1024) {
+                const int blk = e >> 6, ln = (e >> 1) & 31, half = e & 1;
+                const int mb = blk >> 2, nb = blk & 3;
+                tile[(nb * 8 + (ln & 3) * 2 + half) * 33 + mb * 8 + (ln >> 2)] = s;
             } else {
-                if (col < q) dst = sy + col;
+                const int col = colbase + (e - 1024);
+                int64_t off = -1;
+                if (!by) {
+                    if (col < p) off = o_sx + col;
+                } else {
+                    if (col < q) off = o_sy + col;
+                }
+                if (off >= 0) {
+                    if (accumulate) s += dst.p[0][off];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d)
+                        if (d < dst.n) dst.p[d][off] = s;
+                }
             }
         }
-        if (dst) *dst = (accumulate ? *dst : 0.0) + s;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
+            const int cl = idx >> 5, r = idx & 31;
+            if (u.kind == 2 && (r >> 3) > (cl >> 3)) continue;      // below the diagonal: never computed
+            const int row = rowbase + r, col = colbase + cl;
+            int64_t off = -1;
+            if (!ay && !by) {
+                if (row < p && col < p) off = row + (int64_t)col * P;
+            } else if (!ay && by) {
+                if (row < p && col < q) off = o_gxy + row + (int64_t)col * P;
+            } else if (ay && by) {
+                if (row == col && row < q) off = o_gyy + row;
+            }
+            if (off >= 0) {
+                double v = tile[cl * 33 + r];
+                if (accumulate) v += dst.p[0][off];
+#pragma unroll
+                for (int d = 0; d < 8; ++d)
+                    if (d < dst.n) dst.p[d][off] = v;
+            }
+        }
+        if ((u.sums & 2) && threadIdx.x == 0) {
+            double s = 0.0;
+            for (int sg = sbeg; sg < send; ++sg)
+                s += partials[((int64_t)sg * NCW + wu) * UNIT_STRIDE + 1056];
+            if (accumulate) s += dst.p[0][o_sw];
+            for (int d = 0; d < dst.n; ++d) dst.p[d][o_sw] = s;
+        }
     }
-    if ((u.sums & 2) && threadIdx.x == 0) {
-        double s = 0.0;
-        for (int sg = sbeg; sg < send; ++sg)
-            s += partials[((int64_t)sg * NCW + wu) * UNIT_STRIDE + 1056];
-        *sw = (accumulate ? *sw : 0.0) + s;
+    if (dst.done) {
+        __threadfence_system();          // this thread's (remote) stores are performed before what follows
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(dst.done, 1u);
+            if (prev == gridDim.x - 1) {          // every block has fenced its stores
+                *dst.done = 0;
+                __threadfence_system();
+                for (int d = 0; d < dst.n; ++d)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst.flag[d]), "l"(dst.seq) : "memory");
+            }
+        }
     }
 }
 
@@ -903,6 +936,19 @@ int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_
 int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
                 const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
                 double* d_packed, int accumulate) {
+    ReduceDst dst;
+    dst.n = 1;
+    dst.p[0] = d_packed;
+    return launch_gram_to(c, dX, ldx, dY, ldy, dw, n, p, q, d_pivot, dst, accumulate);
+}
+
+int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy,
+                   const double* dw, int64_t n, int64_t p, int64_t q, const double* d_pivot,
+                   const ReduceDst& dst, int accumulate) {
+    if (accumulate && dst.n != 1) {
+        set_error("gram: accumulation needs a single destination");
+        return JCB200_EINVAL;
+    }
     if (((uintptr_t)dX & 15) || ((uintptr_t)dY & 15) || (dw && ((uintptr_t)dw & 15)) || (ldx & 1) ||
         (ldy & 1)) {
         set_error("gram: device pointers must be 16-byte aligned and leading dimensions even "
@@ -1018,7 +1064,7 @@ int launch_gram(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t
     phase_end(c, JCB200_T_GRAM);
     phase_begin(c, JCB200_T_REDUCE);
     gram_reduce_kernel<<<ng * NCW, 256, 0, c->stream>>>(dgroups, dgseg, (const double*)c->partials.p,
-                                                        d_packed, (int)p, (int)q, nbx, accumulate);
+                                                        dst, (int)p, (int)q, nbx, accumulate);
     JCB_LAUNCH_CHECK();
     phase_end(c, JCB200_T_REDUCE);
     return 0;

@@ -31,71 +31,99 @@ constexpr int LV_THREADS = 512;
 constexpr int LV_CLUSTER = 8;
 
 // ----------------------------------------------------------------------------------------- K3
+// Element i of the packed Gram: one buffer, or the sum over the slots of the peer window in rank order.
+__device__ __forceinline__ double packed_at(const PackedSrc& s, int64_t i) {
+    double v = __ldcg(s.base + i);
+    for (int r = 1; r < s.n; ++r) v += __ldcg(s.base + (int64_t)r * s.stride + i);
+    return v;
+}
+
 // stats: delta, means, scales (ONE block), and the non-finite check: a NaN or Inf anywhere in X, Y or the
 // weights reaches the weighted column sums (or their total), so testing p + q + 1 numbers covers the input.
 // sumw[0] = S, sumw[1] = 0 (finite) / 1 (non-finite input: the LV loop is skipped, the host entry points fail
 // with JCB200_ENONFINITE — the reference throws from svd at plskern.jl:154).
-__global__ void finalize_stats_kernel(const double* __restrict__ packed,
-                                      const double* __restrict__ pivot, int p, int q, int scal,
-                                      double* __restrict__ xmeans, double* __restrict__ xscales,
+// Row-sharded fit with the fused exchange: the kernel first waits (acquire, system scope) until every rank's
+// flag of this exchange is up in the own window — the slots then hold all partial Grams — and also writes the
+// SUMMED column sums and sum(w) to `sums` (p + q + 1 doubles) for the second kernel.
+__global__ void finalize_stats_kernel(const PackedSrc src, const double* __restrict__ pivot, int p, int q,
+                                      int scal, double* __restrict__ xmeans, double* __restrict__ xscales,
                                       double* __restrict__ ymeans, double* __restrict__ yscales,
-                                      double* __restrict__ sumw, double* __restrict__ delta) {
+                                      double* __restrict__ sumw, double* __restrict__ delta,
+                                      double* __restrict__ sums) {
     const int64_t P = p, Q = q;
-    const double* gxx = packed;
-    const double* gyy = packed + P * P + P * Q;
-    const double* sx = gyy + Q;
-    const double* sy = sx + P;
-    const double S = sy[Q];
-    int bad = !isfinite(S);
+    int bad = 0;
+    if (src.flags && threadIdx.x < src.n) {
+        const unsigned long long* f = src.flags + threadIdx.x * src.flag_stride;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= src.seq) break;
+            __nanosleep(40);
+            if (clock64() - t0 > 8000000000ll) {       // a peer never arrived (~4 s): fail the fit, do not hang
+                bad = 1;
+                if (src.timeouts) atomicAdd(src.timeouts, 1u);
+                break;
+            }
+        }
+    }
+    bad = __syncthreads_or(bad);
+    const int64_t o_gyy = P * P + P * Q, o_sx = o_gyy + Q, o_sy = o_sx + P;
+    const double S = packed_at(src, o_sy + Q);
+    bad |= !isfinite(S);
     for (int j = threadIdx.x; j < p + q; j += blockDim.x) {
         if (j < p) {
-            bad |= !isfinite(sx[j]);
-            const double d = sx[j] / S;
+            const double sxj = packed_at(src, o_sx + j);
+            bad |= !isfinite(sxj);
+            const double d = sxj / S;
             delta[j] = d;
+            sums[j] = sxj;
             xmeans[j] = pivot[j] + d;
             // K1 leaves acc_jj = G_jj + c_j s_j (A operand raw): remove the rank-one term first
-            xscales[j] = scal ? sqrt((gxx[j + (int64_t)j * P] - pivot[j] * sx[j]) / S - d * d) : 1.0;
+            xscales[j] = scal ? sqrt((packed_at(src, j + (int64_t)j * P) - pivot[j] * sxj) / S - d * d) : 1.0;
         } else {
             const int k = j - p;
-            bad |= !isfinite(sy[k]);
-            const double d = sy[k] / S;
+            const double syk = packed_at(src, o_sy + k);
+            bad |= !isfinite(syk);
+            const double d = syk / S;
             delta[j] = d;
+            sums[j] = syk;
             ymeans[k] = pivot[j] + d;
-            yscales[k] = scal ? sqrt((gyy[k] - pivot[j] * sy[k]) / S - d * d) : 1.0;
+            yscales[k] = scal ? sqrt((packed_at(src, o_gyy + k) - pivot[j] * syk) / S - d * d) : 1.0;
         }
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
+        sums[p + q] = S;
         sumw[0] = S;
         sumw[1] = bad ? 1.0 : 0.0;
     }
 }
 
 // XtX (full, mirrored) and XtY, centred exactly and scaled
-__global__ void finalize_gram_kernel(const double* __restrict__ packed,
-                                     const double* __restrict__ pivot,
-                                     const double* __restrict__ delta,
+__global__ void finalize_gram_kernel(const PackedSrc src, const double* __restrict__ pivot,
+                                     const double* __restrict__ delta, const double* __restrict__ sums,
                                      const double* __restrict__ xscales,
                                      const double* __restrict__ yscales, int p, int q,
                                      double* __restrict__ XtX, double* __restrict__ XtY) {
-    const int64_t P = p, Q = q;
-    const double* sx = packed + P * P + P * Q + Q;
-    const double* sy = sx + P;
-    const double S = sy[Q];
+    const int64_t P = p;
+    const double* sx = sums;
+    const double* sy = sums + p;
+    const double S = sums[p + q];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // row
     const int j = blockIdx.y;                              // column of [XtX | XtY]
     if (i >= p) return;
     if (j < p) {
         if (i > j) return;
         // K1: acc_ij = G_ij + c_i s_j (A operand raw, B operand centred about the pivot c)
-        const double v = ((packed[i + (int64_t)j * P] - pivot[i] * sx[j]) / S - delta[i] * delta[j]) /
+        const double v = ((packed_at(src, i + (int64_t)j * P) - pivot[i] * sx[j]) / S - delta[i] * delta[j]) /
                          (xscales[i] * xscales[j]);
         XtX[i + (int64_t)j * P] = v;
         XtX[j + (int64_t)i * P] = v;
     } else {
         const int k = j - p;
         XtY[i + (int64_t)k * P] =
-            ((packed[P * P + i + (int64_t)k * P] - pivot[i] * sy[k]) / S - delta[i] * delta[p + k]) /
+            ((packed_at(src, P * P + i + (int64_t)k * P) - pivot[i] * sy[k]) / S - delta[i] * delta[p + k]) /
             (xscales[i] * yscales[k]);
     }
 }
@@ -940,22 +968,34 @@ int launch_solve(Ctx* c, const double* d_packed, const double* d_pivot, int64_t 
                  int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
                  double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
                  double* dsumw) {
-    // workspace: XtX p*p | XtY p*q | delta p+q | zp 2p | Ppriv, Rpriv LV_CLUSTER*p*nlv each (8-CTA form only)
-    const size_t need = (size_t)(p * p + p * q + (p + q) + 2 * p + 2 * (size_t)LV_CLUSTER * p * nlv) * 8;
+    PackedSrc src;
+    src.base = d_packed;
+    src.n = 1;
+    return launch_solve_src(c, src, d_pivot, p, q, nlv, scal, dP, dR, dW, dC, dTT, dxmeans, dxscales, dymeans,
+                            dyscales, dsumw);
+}
+
+int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_t p, int64_t q,
+                     int nlv, int scal, double* dP, double* dR, double* dW, double* dC, double* dTT,
+                     double* dxmeans, double* dxscales, double* dymeans, double* dyscales,
+                     double* dsumw) {
+    // workspace: XtX p*p | XtY p*q | delta p+q | sums p+q+2 | zp 2p | Ppriv, Rpriv LV_CLUSTER*p*nlv each (8-CTA form)
+    const size_t need = (size_t)(p * p + p * q + 2 * (p + q) + 2 + 2 * p + 2 * (size_t)LV_CLUSTER * p * nlv) * 8;
     JCB_TRY(ensure(c->solve_ws, need));
     double* XtX = (double*)c->solve_ws.p;
     double* XtY = XtX + p * p;
     double* delta = XtY + p * q;
-    double* zp = delta + (p + q);
+    double* sums = delta + (p + q);
+    double* zp = sums + (p + q + 2);
     double* Ppriv = zp + 2 * p;
     double* Rpriv = Ppriv + (size_t)LV_CLUSTER * p * nlv;
 
     phase_begin(c, JCB200_T_FINALIZE);
     finalize_stats_kernel<<<1, 512, 0, c->stream>>>(
-        d_packed, d_pivot, (int)p, (int)q, scal, dxmeans, dxscales, dymeans, dyscales, dsumw, delta);
+        src, d_pivot, (int)p, (int)q, scal, dxmeans, dxscales, dymeans, dyscales, dsumw, delta, sums);
     JCB_LAUNCH_CHECK();
     dim3 grid((unsigned)((p + 127) / 128), (unsigned)(p + q));
-    finalize_gram_kernel<<<grid, 128, 0, c->stream>>>(d_packed, d_pivot, delta, dxscales, dyscales, (int)p,
+    finalize_gram_kernel<<<grid, 128, 0, c->stream>>>(src, d_pivot, delta, sums, dxscales, dyscales, (int)p,
                                                       (int)q, XtX, XtY);
     JCB_LAUNCH_CHECK();
     phase_end(c, JCB200_T_FINALIZE);

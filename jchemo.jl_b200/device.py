@@ -118,6 +118,20 @@ def comm_allreduce_dev(packed):
     _lib.check(_lib.lib().jcb200_comm_allreduce_dev(_p(packed), packed.numel()), "comm_allreduce_dev")
 
 
+def comm_gram_dev(X, Y, w, n, pivot):
+    """K1 + K1b with the reduced block written straight into every rank's peer window (fused exchange)."""
+    _lib.check(_lib.lib().jcb200_comm_gram_dev(_p(X), _ld(X), _p(Y), _ld(Y), _p(w), n, X.shape[0], Y.shape[0],
+                                               _p(pivot)), "comm_gram_dev")
+
+
+def comm_solve_dev(pivot, model, scal=False):
+    """K3 on the sum of the window's slots (after the flags of this exchange) + K4."""
+    _lib.check(_lib.lib().jcb200_comm_solve_dev(
+        _p(pivot), model.p, model.q, model.nlv, int(scal), _p(model.P), _p(model.R), _p(model.W), _p(model.C),
+        _p(model.TT), _p(model.xmeans), _p(model.xscales), _p(model.ymeans), _p(model.yscales), _p(model.sumw)),
+        "comm_solve_dev")
+
+
 def solve_dev(packed, pivot, model, scal=False):
     _lib.check(_lib.lib().jcb200_solve_dev(
         _p(packed), _p(pivot), model.p, model.q, model.nlv, int(scal), _p(model.P), _p(model.R),

@@ -91,17 +91,25 @@ class PeerComm:
     def allreduce(self, packed):
         dev.comm_allreduce_dev(packed)
 
+    def gram(self, X, Y, w, n_local, pivot):
+        dev.comm_gram_dev(X, Y, w, n_local, pivot)
+
+    def solve(self, pivot, model, scal=False):
+        dev.comm_solve_dev(pivot, model, scal)
+
     def close(self):
         from . import _lib
         _lib.check(_lib.lib().jcb200_comm_destroy(), "comm_destroy")
 
 
-def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None, comm=None):
+def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, packed=None, comm=None, fused=True):
     """X [p, ld], Y [q, ld], w [n_local] or None hold this rank's rows on its GPU.  The library's kernels and
     the collectives must share one stream: the fit is issued on torch's CURRENT stream (the library is switched
     to it here).  `comm`: a PeerComm (peer-HBM exchange) — else torch.distributed (NCCL / gloo) carries the
-    pivot broadcast and the packed all-reduce.  A rank may hold no rows (n_local == 0): it contributes zeros and
-    still takes part in the exchange."""
+    pivot broadcast and the packed all-reduce.  With a PeerComm the exchange is FUSED by default: K1b stores the
+    reduced block into every rank's window and K3 reads the sum of the slots (`fused=False`: separate push and
+    sum kernels on `packed`).  A rank may hold no rows (n_local == 0): it contributes zeros and still takes part
+    in the exchange."""
     dev.use_current_stream()
     p, q = X.shape[0], Y.shape[0]
     if pivot is None:
@@ -115,15 +123,19 @@ def fit_sharded(X, Y, w, n_local, model, scal=False, group=None, pivot=None, pac
         if rank == 0:
             dev.pivot_dev(X, Y, n_local, pivot)
         broadcast_pivot(pivot, group)
-    if n_local > 0:
-        dev.gram_dev(X, Y, w, n_local, pivot, packed)
+    if comm is not None and fused:
+        comm.gram(X, Y, w, n_local, pivot)      # K1b writes into every rank's window: the exchange is the store
+        comm.solve(pivot, model, scal)          # K3 reads the sum of the slots once the flags are up
     else:
-        packed.zero_()
-    if comm is not None:
-        comm.allreduce(packed)
-    else:
-        reduce_packed(packed, group)
-    dev.solve_dev(packed, pivot, model, scal)
+        if n_local > 0:
+            dev.gram_dev(X, Y, w, n_local, pivot, packed)
+        else:
+            packed.zero_()
+        if comm is not None:
+            comm.allreduce(packed)
+        else:
+            reduce_packed(packed, group)
+        dev.solve_dev(packed, pivot, model, scal)
     if n_local > 0:
         if model.nlv > 0:
             dev.scores_dev(X, n_local, model, pivot=pivot)
