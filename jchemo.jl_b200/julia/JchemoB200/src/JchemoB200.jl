@@ -9,8 +9,9 @@ or a B200 every call raises.
 
 The library path is taken from `ENV["JCHEMO_B200_LIB"]`, else `libjchemo_b200.so` next to this package.
 
-NOTE: this file could not be executed in the build container (no Julia toolchain there); the same ABI
-is exercised end to end by the Python ctypes mirror in `jchemo.jl_b200/plskern.py` and `tests/`.
+NOTE: this file could not be executed in the build container (no Julia toolchain there, nor on the GPU boxes);
+its `ccall` signatures are checked statically against the header (tests/test_abi.py) and the same ABI is
+exercised end to end by the Python ctypes mirror in `jchemo.jl_b200/plskern.py` and `tests/`.
 """
 module JchemoB200
 
@@ -18,6 +19,7 @@ using LinearAlgebra
 using Libdl
 
 export Plsr, plskern, plskern!, transform, coef, predict, gridscorelv, gridcvlv, locwlv, xfit, xfit!, xresid, xresid!
+export pin!, unpin!, resident, resident_add, resident_drop, last_fit_info
 
 const LIB = get(ENV, "JCHEMO_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "..", "..", "libjchemo_b200.so")))
@@ -56,7 +58,81 @@ dense64(X) = X isa Matrix{Float64} ? X : Matrix{Float64}(X)
 function check(rc::Cint, what::AbstractString)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:jcb200_last_error, LIB), Cstring, ()))
+    # JCB200_ENONFINITE: the reference fails inside LinearAlgebra.svd with this very exception (plskern.jl:154)
+    rc == -5 && throw(ArgumentError("matrix contains Infs or NaNs ($what: $msg)"))
     error("JchemoB200.$what failed (status $rc): $msg")
+end
+
+# ---------------------------------------------------------------- host memory the GPU can reach at PCIe speed
+# Large OUTPUTS (the scores T, the normalised weights) are taken from the library's page-locked pool
+# (jcb200_host_alloc): the device-to-host copy then runs at link speed instead of through the pageable staging
+# path.  They are ordinary `Matrix{Float64}` / `Vector{Float64}` for every consumer; the block goes back to the
+# pool when the array is garbage collected.  Small arrays and a failed pool allocation fall back to `undef` arrays.
+const PINNED_MIN_BYTES = 1 << 22
+function pooled(dims::Int...)
+    bytes = 8 * prod(dims)
+    if bytes >= PINNED_MIN_BYTES
+        ptr = ccall((:jcb200_host_alloc, LIB), Ptr{Cvoid}, (Int64,), bytes)
+        if ptr != C_NULL
+            A = unsafe_wrap(Array, Ptr{Float64}(ptr), dims; own = false)
+            finalizer(_ -> ccall((:jcb200_host_free, LIB), Cint, (Ptr{Cvoid},), ptr), A)
+            return A
+        end
+    end
+    Array{Float64}(undef, dims...)
+end
+
+"""
+    pin!(X) ; unpin!(X)
+
+Page-lock a caller's `Array{Float64}` in place (`jcb200_host_register`): later fits / predictions on it copy at
+full PCIe speed (C2: 81 ms instead of 98 ms end to end).  Worth it for an X that is used more than once;
+`unpin!` before the array is freed.
+"""
+pin!(X::Array{Float64}) = (check(ccall((:jcb200_host_register, LIB), Cint, (Ptr{Cvoid}, Int64), X, sizeof(X)), "pin!"); X)
+unpin!(X::Array{Float64}) = (check(ccall((:jcb200_host_unregister, LIB), Cint, (Ptr{Cvoid},), X), "unpin!"); X)
+
+"""
+    resident_add(X) ; resident_drop(X) ; resident(f, X, Y, ...)
+
+Device-resident data handle (`jcb200_resident_add`): upload a matrix once; every later call that is handed this
+very array as `X` (or `Y`) skips the host-to-device transfer — `plskern`, `summary`, `transform`, `predict`,
+`gridscorelv`, `gridcvlv`, `xfit`.  Do not modify the array on the host while it is resident.
+
+    resident(X, Y) do
+        fm = plskern(X, Y; nlv = 25)
+        summary(fm, X)
+        gridscorelv(X, Y, X, Y; score = :rmsep, nlv = 0:25)
+    end
+"""
+resident_add(X::Matrix{Float64}) =
+    (check(ccall((:jcb200_resident_add, LIB), Cint, (Ptr{Float64}, Int64, Int64, Int64), X, max(nro(X), 1), nro(X), nco(X)),
+           "resident_add"); X)
+resident_drop(X::Matrix{Float64}) = (ccall((:jcb200_resident_drop, LIB), Cint, (Ptr{Float64},), X); nothing)
+function resident(f::Function, mats::Matrix{Float64}...)
+    done = Matrix{Float64}[]
+    try
+        for A in mats
+            resident_add(A)
+            push!(done, A)
+        end
+        return f()
+    finally
+        foreach(resident_drop, done)
+    end
+end
+
+"""
+    last_fit_info()
+
+`(nlv_effective = k,)` for the calling thread's last fit: LVs that carry information (`TT[a] > 0`).  Where the
+reference divides 0/0 (constant y, more LVs than the data carry; plskern.jl:152,166) this library returns inert
+LVs — finite model, predictions equal to those of the last informative LV.
+"""
+function last_fit_info()
+    k = Ref{Int32}(0)
+    check(ccall((:jcb200_last_fit_info, LIB), Cint, (Ref{Int32},), k), "last_fit_info")
+    (nlv_effective = Int(k[]),)
 end
 
 """
@@ -78,12 +154,12 @@ function _fit(X::Matrix{Float64}, Y::Matrix{Float64}, weights, nlv::Integer, sca
     a = max(0, min(n, p, nlv))                                      # :116
     w = weights === nothing ? nothing : Vector{Float64}(vec(weights))
     w === nothing || length(w) == n || throw(DimensionMismatch("weights has length $(length(w))"))
-    T = Matrix{Float64}(undef, n, a); P = Matrix{Float64}(undef, p, a)
+    T = pooled(n, a); P = Matrix{Float64}(undef, p, a)
     R = Matrix{Float64}(undef, p, a); W = Matrix{Float64}(undef, p, a)
     C = Matrix{Float64}(undef, q, a); TT = Vector{Float64}(undef, a)
     xmeans = Vector{Float64}(undef, p); xscales = Vector{Float64}(undef, p)
     ymeans = Vector{Float64}(undef, q); yscales = Vector{Float64}(undef, q)
-    wout = Vector{Float64}(undef, n)
+    wout = pooled(n)
     nlv_out = Ref{Int32}(0)
     rc = ccall((:jcb200_plskern_fit, LIB), Cint,
                (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int32, Int32,
@@ -114,6 +190,12 @@ Same as `Jchemo.plskern!` (src/plskern.jl:112-178): X and Y leave centred (and s
 function plskern!(X::Matrix{Float64}, Y::Matrix{Float64}, weights = nothing; nlv, scal = false)
     _fit(X, Y, weights, nlv, scal, true)
 end
+# The reference's signature is `plskern!(X::Matrix, Y::Matrix, ...)`; with a non-Float64 element type its in-place
+# centring (`center!`, utility.jl:76-81) throws an InexactError (integers) or computes in another precision.  The
+# device path is Float64 only: say so instead of converting behind the caller's back (the side effect could not
+# reach the caller's array).
+plskern!(X::Matrix, Y::Matrix, weights = nothing; nlv, scal = false) =
+    throw(ArgumentError("plskern! needs Matrix{Float64} arguments (got $(eltype(X)), $(eltype(Y))); use plskern"))
 
 # ---------------------------------------------------------------- transform (src/plskern.jl:187-195)
 function transform(object::Plsr, X; nlv = nothing)
@@ -123,7 +205,7 @@ function transform(object::Plsr, X; nlv = nothing)
     nlv = max(nlv, 0)
     m, p = size(X)
     p == nro(object.R) || throw(DimensionMismatch("X has $p columns, the model has $(nro(object.R))"))
-    T = Matrix{Float64}(undef, m, nlv)
+    T = pooled(m, nlv)
     (nlv == 0 || m == 0) && return T
     rc = ccall((:jcb200_transform, LIB), Cint,
                (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32,
@@ -159,7 +241,7 @@ function predict(object::Plsr, X; nlv = nothing)
     m, p = size(X)
     q = nro(object.C)
     p == length(object.xmeans) || throw(DimensionMismatch("X has $p columns"))
-    pred = [Matrix{Float64}(undef, m, q) for _ in 1:le_nlv]
+    pred = [pooled(m, q) for _ in 1:le_nlv]
     if le_nlv > 0 && m > 0
         ptrs = [pointer(z) for z in pred]
         GC.@preserve pred begin
@@ -183,7 +265,7 @@ end
 Explained X-variance per LV, as `Jchemo`'s `Base.summary(::Plsr, X)`: returns
 `(explvarx = (nlv, var, pvar, cumpvar),)` (NamedTuple of columns; wrap in `DataFrame` as needed).
 """
-function Base.summary(object::Plsr, X::Union{AbstractVector, AbstractMatrix})
+function Base.summary(object::Plsr, X)       # the reference takes Union{Matrix, DataFrame} (plskern.jl:246)
     X = dense64(ensure_mat(X))
     n, a = size(object.T)
     p = nco(X)
