@@ -9,12 +9,13 @@
 //  * X, Y are column-major (rows contiguous) so the contraction dimension K = rows is contiguous for
 //    both operands.  The augmented column space is cut into 32-column blocks (X blocks, then Y blocks);
 //    a 32x32 output "unit" (block_a, block_b) is owned by one warp: 16 DMMA.8x8x4 accumulators.
-//  * A CTA (16 consumer warps + 1 TMA producer warp) works on a "group": up to 8 column blocks staged
-//    per pipeline stage and up to 16 units on them (an off-diagonal 128x128 super-tile, or a diagonal
-//    super-tile + the X'Y / Y'Y units).  Diagonal units skip the 8x8 blocks below the diagonal.
-//  * Rows are streamed in stages of KT = 40 rows by 2-D TMA (FP64 tensor map, zero fill out of
-//    bounds) into a [column][KT] shared-memory tile; KT = 40 makes the 128-bit fragment loads
-//    bank-conflict free.  Full/empty mbarriers form a 2-stage ring.
+//  * A CTA (16 warps; thread 0 doubles as the TMA producer and polls the ring between k8-steps) works on a
+//    "group": two ranges of up to 4 consecutive column blocks staged per pipeline stage and up to 16 units on them
+//    (an off-diagonal 128x128 super-tile, or a diagonal super-tile + the X'Y / Y'Y units).  Diagonal units skip the
+//    8x8 blocks below the diagonal.
+//  * Rows are streamed in stages of KT = 56 rows: two 2-D TMA loads per stage (FP64 tensor map, box 56 rows x 128
+//    columns, zero fill out of bounds) into a [column][KT] shared-memory tile; KT = 8 (mod 16) makes the 128-bit
+//    fragment loads bank-conflict free.  Full/empty mbarriers form a 2-stage ring (2 x 114 KB).
 //  * Centring (x - c, c = strided-sample pivot) and weighting happen on the fragments in registers;
 //    the exact correction G - delta delta' is applied in K3.  Zero-filled tail rows get weight 0.
 //  * Weighted stream-K: the (group, stage) space is cut into equal-cost contiguous pieces, one per SM,

@@ -131,6 +131,7 @@ _C_TO_JULIA = {
     "int32_t*": {"Ref{Int32}", "Ptr{Int32}", "Ptr{Cint}"}, "const int*": {"Ptr{Cint}", "Ptr{Int32}"},
     "const int32_t*": {"Ptr{Cint}", "Ptr{Int32}"},
     "const int64_t*": {"Ptr{Int64}"}, "double* const*": {"Ptr{Ptr{Float64}}"}, "void*": {"Ptr{Cvoid}"},
+    "const void*": {"Ptr{Cvoid}"},
 }
 
 
@@ -140,8 +141,13 @@ def test_julia_ccall_signatures_match_the_header():
     protos = _header_prototypes()
     src = open(os.path.join(ROOT, "jchemo.jl_b200", "julia", "JchemoB200", "src", "JchemoB200.jl")).read()
     calls = re.findall(r"ccall\(\(:(jcb200_\w+),\s*LIB\),\s*(\w+),\s*\(([^)]*)\)", src)
-    assert len(calls) >= 10
-    for name, ret, argt in calls:
+    assert len(calls) >= 14
+    # the in-Jchemo binding of INTEGRATION.md (jchemo_binding/plskern_b200.jl) is held to the same check
+    src2 = open(os.path.join(ROOT, "jchemo.jl_b200", "julia", "jchemo_binding", "plskern_b200.jl")).read()
+    calls2 = re.findall(r"ccall\(\(:(jcb200_\w+),\s*LIBB200\),\s*(\w+),\s*\(([^)]*)\)", src2)
+    assert {c[0] for c in calls2} >= {"jcb200_plskern_fit", "jcb200_transform", "jcb200_coef", "jcb200_predict_sweep",
+                                      "jcb200_init", "jcb200_init_multi"}
+    for name, ret, argt in calls + calls2:
         assert name in protos, f"{name} is not declared in include/jchemo_b200.h"
         jl = [t.strip() for t in argt.replace("\n", " ").split(",") if t.strip()]
         ct = protos[name]
