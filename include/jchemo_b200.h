@@ -206,7 +206,7 @@ int jcb200_summary(const double* X, int64_t ldx, int64_t n, int64_t p, const dou
  * the single buffer a row-sharded fit all-reduces (sum) across GPUs. */
 int64_t jcb200_packed_len(int64_t p, int64_t q);
 
-/* Strided-sample pivot c (p+q+1 doubles, device): column means of up to 16384 evenly spaced rows of
+/* Strided-sample pivot c (p+q+1 doubles, device): column means of up to 4096 evenly spaced rows of
  * the shard, or all zeros when every column has mean^2 <= 64 variance (centring then costs more
  * FP64-pipe cycles than it saves digits); element p+q is 1.0 when centring is on, 0.0 otherwise.
  * Multi-GPU: rank 0 computes it and broadcasts, so all partial Grams share one pivot. */

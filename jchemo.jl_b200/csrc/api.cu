@@ -566,6 +566,7 @@ static void destroy_ctx(Ctx* c) {
     free_buf(c->partials);
     free_buf(c->sched_dev);
     free_buf(c->pivot_ws);
+    c->pivot_ctr_zeroed = c->pivot_ctr_base = nullptr;
     free_buf(c->coef_ws);
     free_buf(c->locw_ws);
     free_buf(c->solve_ws);

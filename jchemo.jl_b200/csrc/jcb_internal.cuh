@@ -69,6 +69,8 @@ struct Ctx {
     size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf pivot_ws;
+    void* pivot_ctr_zeroed = nullptr;   // where the pivot kernel's completion counter was last zeroed
+    void* pivot_ctr_base = nullptr;     // ... and the workspace allocation it lived in
     Buf pivot_sample;               // device copy of the host row sample the streamed fit takes its pivot from
     void* pivot_host = nullptr;     // page-locked staging of that sample
     size_t pivot_host_bytes = 0;

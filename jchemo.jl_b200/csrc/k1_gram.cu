@@ -118,7 +118,7 @@ struct GramParams {
 //  * The A operand (rows of G) is used RAW; only the B operand is centred (and weighted):
 //      acc_ij = sum_k x_ki * w_k (x_kj - c_j)  =  G_ij + c_i s_j ,  s_j = sum_k w_k (x_kj - c_j)
 //    K3 subtracts the rank-one term c_i s_j exactly (s is accumulated by the diagonal units); with the
-//    16K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
+//    4K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
 //    compete with DMMA for the FP64 pipe.
 //  * DIAG units skip the 8x8 blocks below the diagonal and accumulate the column sums; NBC < 4 (edge
 //    and Y blocks) skips empty column blocks; MASKED is the zero-filled tail stage of the unweighted
@@ -574,20 +574,31 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
     }
 }
 
-// Strided-sample pivot: mean of up to 16384 rows per column, taken as 16 evenly spaced chunks of 1024
-// consecutive rows (coalesced 2 KB reads; 16 pages per column instead of 64: the kernel is TLB-miss bound).  One block per column.  The pivot only has to be CLOSE to
-// the mean (K3 corrects exactly); a large sample keeps the correction terms c_i s_j and delta delta'
-// far below the rounding level even for offset-heavy data.  ratio[col] = mean^2 / variance of the
-// sample tells how much centring matters for this column.
+// Strided-sample pivot: mean of up to 4096 rows per column, taken as 16 evenly spaced chunks of 256 consecutive
+// rows (coalesced 2 KB reads), all 16 loads of a thread in flight at once: the kernel is a chain of memory / TLB
+// latencies, not of bytes (16 K rows in 8 dependent rounds took 15 us; one round takes ~4).  One block per column.
+// The pivot only has to be CLOSE to the mean (K3 corrects exactly): with 4096 rows the correction terms c_i s_j
+// and delta delta' stay ~sigma/64 relative, far below the rounding level even for offset-heavy data.
+// ratio[col] = mean^2 / variance of the sample tells how much centring matters for this column.
+//
+// The LAST block to finish takes the data-dependent centring decision (it used to be a kernel of its own):
+// centring costs FP64-pipe cycles that the DMMAs need; when every column has mean^2 <= 64 variance, second
+// moments about 0 lose at most ~2 digits to the mean (K3 removes it exactly: pivot = 0 is just another pivot),
+// far inside the 1e-10 budget.  pivot[p + q] = 1 (the data need centring), 0 (they do not, and the pivot was
+// zeroed: K1 runs without centring; only with JCB_AUTO_NOCENTER=1, because K1 itself gains nothing from it) or
+// 2 (they do not, but K1 keeps its pivot: the default).  K1 centres whenever the flag is non-zero; the score
+// pass K5, where a DADD beside the DMMAs does cost a DMMA slot, goes centre-free on 0 and 2 (k5_xmul.cu).
 __global__ void __launch_bounds__(256)
 pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
-             int64_t n, int p, int q, double* __restrict__ pivot, double* __restrict__ ratio) {
+             int64_t n, int p, int q, double* __restrict__ pivot, double* __restrict__ ratio,
+             unsigned int* __restrict__ counter, int force_center) {
     const int col = blockIdx.x;
     const double* src = col < p ? X + (int64_t)col * ldx : Y + (int64_t)(col - p) * ldy;
     __shared__ double red[16];
+    __shared__ int s_last, s_need;
     double s = 0.0, s2 = 0.0;
     int64_t cnt;
-    if (n <= 16384) {
+    if (n <= 4096) {
         cnt = n;
         for (int64_t i = threadIdx.x; i < n; i += 256) {
             const double v = src[i];
@@ -595,13 +606,15 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
             s2 += v * v;
         }
     } else {
-        cnt = 16384;
-        const int64_t stride = n / 16;             // chunk c covers rows [c*stride, c*stride + 1024)
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) {
-            const double v = src[(c >> 2) * stride + (c & 3) * 256 + threadIdx.x];
-            s += v;
-            s2 += v * v;
+        cnt = 4096;
+        const int64_t stride = n / 16;             // chunk c covers rows [c*stride, c*stride + 256)
+        double v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = src[c * stride + threadIdx.x];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            s += v[c];
+            s2 += v[c] * v[c];
         }
     }
 #pragma unroll
@@ -625,27 +638,27 @@ pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict
         pivot[col] = m;
         // a (near-)constant column has no usable variance estimate: always centre
         ratio[col] = (var > 1e-12 * (m * m) && var > 0.0) ? (m * m) / var : 1e300;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        s_need = 0;
     }
-}
-
-// Centring costs FP64-pipe cycles that the DMMAs need.  When every column has mean^2 <= 64 variance,
-// second moments about 0 lose at most ~2 digits to the mean (K3 removes it exactly: pivot = 0 is just
-// another pivot), far inside the 1e-10 budget, so the pivot is zeroed and K1 runs without centring.
-// pivot[p + q] = 1 (the data need centring), 0 (they do not, and the pivot was zeroed: K1 runs without
-// centring; only with JCB_AUTO_NOCENTER=1, because K1 itself gains nothing from it) or 2 (they do not, but
-// K1 keeps its pivot: the default).  K1 centres whenever the flag is non-zero; the score pass K5, where a
-// DADD beside the DMMAs does cost a DMMA slot, goes centre-free on 0 and 2 (k5_xmul.cu).
-__global__ void pivot_decide_kernel(double* __restrict__ pivot, const double* __restrict__ ratio,
-                                    int ncol, int force_center) {
-    __shared__ int need;
-    if (threadIdx.x == 0) need = 0;
     __syncthreads();
-    for (int c = threadIdx.x; c < ncol; c += blockDim.x)
-        if (!(ratio[c] <= 64.0)) need = 1;
+    if (!s_last) return;
+    // ---- last block: every column's ratio is visible (fence + counter)
+    __threadfence();
+    const int ncol = p + q;
+    int need = 0;
+    for (int c = threadIdx.x; c < ncol; c += 256)
+        if (!(__ldcg(ratio + c) <= 64.0)) need = 1;
+    if (need) s_need = 1;
     __syncthreads();
+    need = s_need;
     if (!need && !force_center)
-        for (int c = threadIdx.x; c < ncol; c += blockDim.x) pivot[c] = 0.0;
-    if (threadIdx.x == 0) pivot[ncol] = need ? 1.0 : (force_center ? 2.0 : 0.0);
+        for (int c = threadIdx.x; c < ncol; c += 256) pivot[c] = 0.0;
+    if (threadIdx.x == 0) {
+        pivot[ncol] = need ? 1.0 : (force_center ? 2.0 : 0.0);
+        *counter = 0;                               // ready for the next launch
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -916,7 +929,7 @@ extern "C" int jcb200_debug_trace(long long* host, int n) {
 
 int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_t ldy, int64_t n,
                  int64_t p, int64_t q, double* d_pivot) {
-    JCB_TRY(ensure(c->pivot_ws, (size_t)(p + q) * 8));
+    JCB_TRY(ensure(c->pivot_ws, (size_t)(p + q) * 8 + 16));
     // Measured on B200 (profiles/k1_r01_notes.md): the centring-free loop is NOT faster (8.65 vs 8.45 ms
     // at C2 — the loop is bound by LDS -> DMMA issue latency, not by the 8 DADDs per k8-step), so
     // centring stays on unless JCB_AUTO_NOCENTER=1 asks for the data-dependent decision.
@@ -925,11 +938,16 @@ int launch_pivot(Ctx* c, const double* dX, int64_t ldx, const double* dY, int64_
         const char* e = getenv("JCB_AUTO_NOCENTER");
         force = (e && atoi(e)) ? 0 : 1;
     }
+    // the completion counter lives behind the ratios; it is zeroed when the workspace is (re)allocated and
+    // resets itself at the end of every launch
+    unsigned int* counter = (unsigned int*)((double*)c->pivot_ws.p + (p + q));
+    if (c->pivot_ctr_zeroed != (void*)counter || c->pivot_ctr_base != c->pivot_ws.p) {
+        JCB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), c->stream));
+        c->pivot_ctr_zeroed = (void*)counter;
+        c->pivot_ctr_base = c->pivot_ws.p;
+    }
     pivot_kernel<<<(int)(p + q), 256, 0, c->stream>>>(dX, ldx, dY, ldy, n, (int)p, (int)q, d_pivot,
-                                                      (double*)c->pivot_ws.p);
-    JCB_LAUNCH_CHECK();
-    pivot_decide_kernel<<<1, 256, 0, c->stream>>>(d_pivot, (const double*)c->pivot_ws.p, (int)(p + q),
-                                                  force);
+                                                      (double*)c->pivot_ws.p, counter, force);
     JCB_LAUNCH_CHECK();
     return 0;
 }
