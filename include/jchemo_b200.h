@@ -106,7 +106,7 @@ int jcb200_resident_drop(const double* A);
 int jcb200_resident_count(void);
 
 /* Facts about the last successful jcb200_plskern_fit of the calling thread: the number of latent variables
- * that carry information (TT[a] > 0).  A degenerate LV — XtY deflated to exactly zero, e.g. constant y or more
+ * that carry information (TT[a] > 0 and C[:, a] != 0).  A degenerate LV — XtY deflated to exactly zero, e.g. constant y or more
  * LVs than the data carry; the reference divides 0/0 at /root/reference/src/plskern.jl:152,166 — is returned
  * inert (w = e_1, c = 0, P = 0), so predictions stay finite and equal those of the last informative LV. */
 int jcb200_last_fit_info(int32_t* nlv_effective);

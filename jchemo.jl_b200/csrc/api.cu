@@ -222,6 +222,17 @@ static void resident_clear(Ctx* c) {
 
 // per-thread facts about the last fit (jcb200_last_fit_info)
 static thread_local int32_t tl_nlv_effective = 0;
+// an LV carries information when its score has variance (tt > 0) and it moves a prediction (c != 0): a degenerate
+// LV (XtY deflated to zero: w = e_1) has c = 0 exactly, one past the rank of X has tt = 0
+static int32_t count_effective_lvs(const double* TT, const double* C, int64_t q, int nlv) {
+    int32_t k = 0;
+    for (int a = 0; a < nlv; ++a) {
+        bool moves = false;
+        for (int64_t j = 0; j < q; ++j) moves |= C[j + (int64_t)a * q] != 0.0;
+        k += (TT[a] > 0.0 && moves) ? 1 : 0;
+    }
+    return k;
+}
 
 // ---- pivot of a streamed host fit: a strided sample over ALL rows (16 evenly spaced blocks of 64 rows), gathered
 // by the host into a small page-locked buffer and sent ahead of the first row chunk.  A pivot taken from the first
@@ -873,8 +884,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     if (g_ndev > 1 && n >= 65536 * (int64_t)g_ndev) {
         const int r = fit_multi_locked(X, ldx, Y, ldy, w, n, p, q, nlv, scal, writeback_xy, T, ldt, P, R, W, C, TT,
                                        xmeans, xscales, ymeans, yscales, w_out);
-        if (r == 0)
-            for (int a = 0; a < nlv; ++a) tl_nlv_effective += TT[a] > 0.0;
+        if (r == 0) tl_nlv_effective = count_effective_lvs(TT, C, q, nlv);
         return r;
     }
     // a matrix registered with jcb200_resident_add is already on the device: no transfer
@@ -1050,7 +1060,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
         set_error("plskern_fit: X, Y or weights contain NaN or Inf");
         return JCB200_ENONFINITE;
     }
-    for (int a = 0; a < nlv; ++a) tl_nlv_effective += TT[a] > 0.0;
+    tl_nlv_effective = count_effective_lvs(TT, C, q, nlv);
     return 0;
 }
 

@@ -125,7 +125,7 @@ end
 """
     last_fit_info()
 
-`(nlv_effective = k,)` for the calling thread's last fit: LVs that carry information (`TT[a] > 0`).  Where the
+`(nlv_effective = k,)` for the calling thread's last fit: LVs that carry information (`TT[a] > 0` and `C[:, a] != 0`).  Where the
 reference divides 0/0 (constant y, more LVs than the data carry; plskern.jl:152,166) this library returns inert
 LVs — finite model, predictions equal to those of the last informative LV.
 """

@@ -123,7 +123,7 @@ def _fit(X, Y, weights, nlv, scal, writeback):
 
 
 def last_fit_info():
-    """Facts about the calling thread's last fit: `nlv_effective` = LVs that carry information (TT > 0);
+    """Facts about the calling thread's last fit: `nlv_effective` = LVs that carry information (TT > 0 and C != 0);
     degenerate LVs (the reference divides 0/0 at plskern.jl:152,166) are returned inert."""
     k = C.c_int32(0)
     _lib.check(_lib.lib().jcb200_last_fit_info(C.byref(k)), "last_fit_info")
