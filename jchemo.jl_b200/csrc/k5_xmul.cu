@@ -90,26 +90,15 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
 // are consumers: one row per thread, every second response per warp.
 template <bool SWEEP, int NCW>
 __host__ __device__ constexpr int xm_epw() { return SWEEP ? NCW : 0; }
-// The 1-2 output columns left over after the 8-column DMMA blocks (nlv = 25 -> 3 blocks + 1) are plain dot
-// products.  Issued from the consumer warps their DFMAs queue behind the DMMAs on the shared FP64 pipe and stall
-// the warp that issued them: 1.4 % of the instructions drew 33 % of the stall samples (ncu, round 2) and kept the
-// pipe at 80 %.  They run on their OWN warps instead, one per SM sub-partition, reading the same staged tile:
-// the consumers issue nothing but LDS + DMMA.
-#ifndef JCB_XM_GEMV_WARPS
-#define JCB_XM_GEMV_WARPS 4
-#endif
-template <int NEX>
-__host__ __device__ constexpr int xm_ngw() { return NEX > 0 ? JCB_XM_GEMV_WARPS : 0; }
 
 template <int NPB, int NEX, bool SWEEP, int NCW>
-__global__ void __launch_bounds__((NCW + 1 + xm_epw<SWEEP, NCW>() + xm_ngw<NEX>()) * 32, XM_OCC)
+__global__ void __launch_bounds__((NCW + 1 + xm_epw<SWEEP, NCW>()) * 32, XM_OCC)
 xmul_kernel(const XmulParams prm) {
     constexpr int XM_NCW = NCW;
     constexpr int XM_MT = 16 * NCW;
     constexpr int XM_PITCH = XM_MT + 4;
     constexpr int XM_EPW = xm_epw<SWEEP, NCW>();
-    constexpr int XM_NGW = xm_ngw<NEX>();
-    constexpr int XM_THREADS = (NCW + 1 + XM_EPW + XM_NGW) * 32;
+    constexpr int XM_THREADS = (NCW + 1 + XM_EPW) * 32;
     // NPB column blocks go through DMMA; NEX (<= 2) leftover columns are plain DFMA dot products on the
     // A fragments this lane already holds (a whole padded 8-column block for 1-2 columns would cost
     // 1/NPB more DMMA time: at nlv = 25 the score GEMM drops from 4 to 3 blocks)
@@ -154,10 +143,10 @@ xmul_kernel(const XmulParams prm) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], XM_NCW + XM_NGW);
+            mbar_init(&empty[s], XM_NCW);
         }
         if (SWEEP) {
-            mbar_init(tfull, XM_NCW + XM_NGW);
+            mbar_init(tfull, XM_NCW);
             mbar_init(tempty, XM_EPW);
         }
         fence_barrier_init();
@@ -203,83 +192,6 @@ xmul_kernel(const XmulParams prm) {
                     for (int e = lane; e < NPT * XM_MPITCH; e += 32) ms[e] = msrc[e];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[buf]);   // release: generic-proxy writes above
-                }
-            }
-        }
-        return;
-    }
-
-    if constexpr (XM_NGW > 0) if (warp > XM_NCW + XM_EPW) {
-        // ------------------------------------------------------------------ leftover-column warps
-        // warp gw owns XM_MT / XM_NGW rows (RPL consecutive rows per lane); per stage 32 (x RPL x NEX) DFMAs
-        constexpr int GROWS = XM_MT / XM_NGW;
-        constexpr int RPL = GROWS / 32;                   // 2 (256-row tiles) or 1 (128-row tiles)
-        static_assert(RPL == 1 || RPL == 2, "leftover-column warps: 1 or 2 rows per lane");
-        const int gw = warp - (XM_NCW + XM_EPW + 1);
-        const int r0 = gw * GROWS + lane * RPL;
-        uint32_t gn = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++gn) {
-            const int64_t row0 = t * XM_MT;
-            const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
-            double ge[NEX > 0 ? NEX : 1][2][2];           // [column][row][k parity]: independent chains
-#pragma unroll
-            for (int e = 0; e < NEX; ++e)
-#pragma unroll
-                for (int r = 0; r < 2; ++r) ge[e][r][0] = ge[e][r][1] = 0.0;
-            for (int ch = 0; ch < nchunk; ++ch, ++it) {
-                const int buf = it % nstage;
-                mbar_wait(&full[buf], (it / nstage) & 1);
-                const double* xs = reinterpret_cast<const double*>(stage_base + (size_t)buf * STAGE);
-                const double* ms = xs + XM_KC * XM_PITCH;
-                const double* mus = mu_s + ch * XM_KC;
-#pragma unroll 8
-                for (int k = 0; k < XM_KC; ++k) {
-                    double x0, x1 = 0.0;
-                    if (RPL == 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(xs + k * XM_PITCH + r0);
-                        x0 = v.x;
-                        x1 = v.y;
-                    } else {
-                        x0 = xs[k * XM_PITCH + r0];
-                    }
-                    if (center) {
-                        const double mk = mus[k];
-                        x0 -= mk;
-                        x1 -= mk;
-                    }
-#pragma unroll
-                    for (int e = 0; e < NEX; ++e) {
-                        const double b = ms[(NP + e) * XM_MPITCH + k];
-                        ge[e][0][k & 1] = fma(x0, b, ge[e][0][k & 1]);
-                        if (RPL == 2) ge[e][1][k & 1] = fma(x1, b, ge[e][1][k & 1]);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[buf]);
-            }
-            if (SWEEP) {
-                if (gn > 0) mbar_wait(tempty, (gn - 1) & 1);     // the previous tile has been read out
-#pragma unroll
-                for (int e = 0; e < NEX; ++e)
-#pragma unroll
-                    for (int r = 0; r < RPL; ++r)
-                        out_s[(NP + e) * XM_PITCH + r0 + r] = ge[e][r][0] + ge[e][r][1];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tfull);
-            } else {
-#pragma unroll
-                for (int e = 0; e < NEX; ++e) {
-                    const int col = NP + e;
-                    if (col < prm.ncol) {
-#pragma unroll
-                        for (int r = 0; r < RPL; ++r)
-                            if (r0 + r < rows) {
-                                double v = ge[e][r][0] + ge[e][r][1];
-                                if (!center) v += cb_s[col];
-                                if (prm.bias) v += prm.bias[col];
-                                prm.Out[row0 + r0 + r + (int64_t)col * prm.ldo] = v;
-                            }
-                    }
                 }
             }
         }
@@ -339,10 +251,13 @@ xmul_kernel(const XmulParams prm) {
         const int64_t row0 = t * XM_MT;
         const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
         double acc[2][NPB][2];
+        double ex[2][NEX > 0 ? NEX : 1];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int nb = 0; nb < NPB; ++nb) acc[h][nb][0] = acc[h][nb][1] = 0.0;
+#pragma unroll
+            for (int e = 0; e < NEX; ++e) ex[h][e] = 0.0;
         }
         auto chunk_loop = [&](auto cen_tag) {
             constexpr bool CEN = decltype(cen_tag)::value;
@@ -367,6 +282,12 @@ xmul_kernel(const XmulParams prm) {
                         const double b = ms[(nb * 8 + g) * XM_MPITCH + k];
                         dmma(acc[0][nb][0], acc[0][nb][1], a.x, b);
                         dmma(acc[1][nb][0], acc[1][nb][1], a.y, b);
+                    }
+#pragma unroll
+                    for (int e = 0; e < NEX; ++e) {
+                        const double b = ms[(NP + e) * XM_MPITCH + k];
+                        ex[0][e] += a.x * b;
+                        ex[1][e] += a.y * b;
                     }
                 }
                 __syncwarp();
@@ -396,6 +317,18 @@ xmul_kernel(const XmulParams prm) {
                         }
                     }
                 }
+#pragma unroll
+                for (int e = 0; e < NEX; ++e) {
+                    double v = ex[h][e];                  // partial over this lane's k (kk); sum the 4 kk lanes
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int col = NP + e;
+                    if (kk == 0 && row < rows && col < prm.ncol) {
+                        if (!center) v += cb_s[col];
+                        if (prm.bias) v += prm.bias[col];
+                        o[(int64_t)col * prm.ldo] = v;
+                    }
+                }
             }
             continue;
         }
@@ -408,11 +341,20 @@ xmul_kernel(const XmulParams prm) {
                 out_s[(nb * 8 + 2 * kk) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][0];
                 out_s[(nb * 8 + 2 * kk + 1) * XM_PITCH + m0 + 2 * g + h] = acc[h][nb][1];
             }
+#pragma unroll
+        for (int e = 0; e < NEX; ++e)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double v = ex[h][e];                      // partial over this lane's k (kk); sum the 4 kk lanes
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (kk == 0) out_s[(NP + e) * XM_PITCH + m0 + 2 * g + h] = v;
+            }
         __syncwarp();
         const int r = lane & 15, half = lane >> 4;
         const bool rok = (m0 + r) < rows;
         if (!SWEEP) {
-            for (int col = half; col < min(prm.ncol, NP); col += 2) {      // the leftover columns have their own warps
+            for (int col = half; col < prm.ncol; col += 2) {
                 if (rok) {
                     double v = out_s[col * XM_PITCH + m0 + r];
                     if (!center) v += cb_s[col];
@@ -442,7 +384,7 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     constexpr int NP = NPB * 8 + NEX;
     constexpr int XM_MT = 16 * NCW;
     constexpr int XM_PITCH = XM_MT + 4;
-    constexpr int XM_THREADS = (NCW + 1 + xm_epw<SWEEP, NCW>() + xm_ngw<NEX>()) * 32;
+    constexpr int XM_THREADS = (NCW + 1 + xm_epw<SWEEP, NCW>()) * 32;
     const int stage = XM_KC * XM_PITCH * 8 + NP * XM_MPITCH * 8;
     // Results either go through a staging tile in shared memory (128-byte global rows) or straight from the
     // accumulator fragments to global memory.  The direct form is chosen when dropping the staging tile turns a
