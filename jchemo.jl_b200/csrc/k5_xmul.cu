@@ -153,22 +153,33 @@ xmul_kernel(const XmulParams prm) {
     }
     __syncthreads();
 
-    // Every CTA owns ONE contiguous range of rows (a multiple of 16, the rows of a consumer warp) and walks it in
-    // tiles of XM_MT rows; its last tile is ragged and costs in proportion to the warps it keeps busy.  With whole
-    // tiles dealt round-robin the slowest CTA ran ceil(tiles / CTAs) full tiles: 4 instead of 3.3 at 125 000 rows
-    // (a rank's shard of the strong-scaled fit on 8 GPUs).
-    const int64_t per_cta = (((prm.m + gridDim.x - 1) / gridDim.x) + 15) & ~(int64_t)15;
-    const int64_t cta_row0 = min(prm.m, (int64_t)blockIdx.x * per_cta);
-    const int64_t cta_row1 = min(prm.m, cta_row0 + per_cta);
-    const int64_t ntiles = (cta_row1 - cta_row0 + XM_MT - 1) / XM_MT;
+    // Whole tiles of XM_MT rows are dealt round-robin in waves of gridDim.x (at any moment the CTAs read ONE window
+    // of consecutive rows: few DRAM pages / TLB entries live); the rows left after the last full wave are cut into
+    // gridDim.x equal ragged tiles (a multiple of 16 rows, the rows of a consumer warp), which cost in proportion to
+    // the warps they keep busy.  With the tail dealt as whole tiles the slowest CTA ran ceil(tiles / CTAs) of them:
+    // 4 instead of 3.3 at 125 000 rows (a rank's shard of the strong-scaled fit on 8 GPUs).  (One contiguous range
+    // per CTA balances as well but made the HBM-bound uses 4 % slower: 148 distant row windows at once.)
+    const int64_t nwaves = (prm.m / XM_MT) / gridDim.x;
+    const int64_t tail_base = nwaves * gridDim.x * XM_MT;
+    const int64_t per_tail = (((prm.m - tail_base + gridDim.x - 1) / gridDim.x) + 15) & ~(int64_t)15;
+    const int64_t tail_row0 = tail_base + (int64_t)blockIdx.x * per_tail;
+    const int64_t ntiles = nwaves + (tail_row0 < prm.m ? 1 : 0);
+    auto tile_rows = [&](int64_t t, int64_t& row0) -> int {
+        if (t < nwaves) {
+            row0 = (t * gridDim.x + blockIdx.x) * XM_MT;
+            return XM_MT;
+        }
+        row0 = tail_row0;
+        return (int)min(per_tail, prm.m - tail_row0);
+    };
     const int nchunk = prm.nchunk;
     uint32_t it = 0;
 
     if (warp == XM_NCW) {
         // ------------------------------------------------------------------ producer warp
         for (int64_t t = 0; t < ntiles; ++t) {
-            const int64_t row0 = cta_row0 + t * XM_MT;
-            const int rows = (int)min((int64_t)XM_MT, cta_row1 - row0);
+            int64_t row0;
+            const int rows = tile_rows(t, row0);
             // aligned shards have an even leading dimension, so a ragged last tile may copy one padding
             // row (rows rounded up to even: bulk copies move multiples of 16 bytes) and stay in bounds
             const bool bulk = prm.aligned != 0;
@@ -217,8 +228,8 @@ xmul_kernel(const XmulParams prm) {
         const int64_t msz = prm.m * (int64_t)q;
         uint32_t tn = 0;
         for (int64_t t = 0; t < ntiles; ++t, ++tn) {
-            const int64_t row0 = cta_row0 + t * XM_MT;
-            const bool rok = row0 + r < cta_row1;
+            int64_t row0;
+            const bool rok = r < tile_rows(t, row0);
             mbar_wait(tfull, tn & 1);
             for (int j0 = jh; j0 < q; j0 += 16) {
                 double pv[8];
@@ -255,8 +266,8 @@ xmul_kernel(const XmulParams prm) {
     const int g = lane >> 2, kk = lane & 3;
     const int m0 = warp * 16;
     for (int64_t t = 0; t < ntiles; ++t) {
-        const int64_t row0 = cta_row0 + t * XM_MT;
-        const int rows = (int)min((int64_t)XM_MT, cta_row1 - row0);
+        int64_t row0;
+        const int rows = tile_rows(t, row0);
         const bool active = m0 < rows;          // ragged last tile: warps without rows only keep the ring going
         double acc[2][NPB][2];
         double ex[2][NEX > 0 ? NEX : 1];
@@ -425,7 +436,7 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     const int smem = nstage * stage + fixed;
     JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem));
-    // one contiguous row range per CTA (a multiple of 16 rows): every SM takes part as soon as there are 16 rows each
+    // full waves of whole tiles + one ragged tile per CTA: every SM takes part as soon as there are 16 rows each
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((prm.m + 15) / 16, (int64_t)XM_OCC * c->num_sms));
     xmul_kernel<NPB, NEX, SWEEP, NCW><<<grid, XM_THREADS, smem, c->stream>>>(prm);
     JCB_LAUNCH_CHECK();
