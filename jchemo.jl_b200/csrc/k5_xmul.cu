@@ -153,33 +153,15 @@ xmul_kernel(const XmulParams prm) {
     }
     __syncthreads();
 
-    // Whole tiles of XM_MT rows are dealt round-robin in waves of gridDim.x (at any moment the CTAs read ONE window
-    // of consecutive rows: few DRAM pages / TLB entries live); the rows left after the last full wave are cut into
-    // gridDim.x equal ragged tiles (a multiple of 16 rows, the rows of a consumer warp), which cost in proportion to
-    // the warps they keep busy.  With the tail dealt as whole tiles the slowest CTA ran ceil(tiles / CTAs) of them:
-    // 4 instead of 3.3 at 125 000 rows (a rank's shard of the strong-scaled fit on 8 GPUs).  (One contiguous range
-    // per CTA balances as well but made the HBM-bound uses 4 % slower: 148 distant row windows at once.)
-    const int64_t nwaves = (prm.m / XM_MT) / gridDim.x;
-    const int64_t tail_base = nwaves * gridDim.x * XM_MT;
-    const int64_t per_tail = (((prm.m - tail_base + gridDim.x - 1) / gridDim.x) + 15) & ~(int64_t)15;
-    const int64_t tail_row0 = tail_base + (int64_t)blockIdx.x * per_tail;
-    const int64_t ntiles = nwaves + (tail_row0 < prm.m ? 1 : 0);
-    auto tile_rows = [&](int64_t t, int64_t& row0) -> int {
-        if (t < nwaves) {
-            row0 = (t * gridDim.x + blockIdx.x) * XM_MT;
-            return XM_MT;
-        }
-        row0 = tail_row0;
-        return (int)min(per_tail, prm.m - tail_row0);
-    };
+    const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
     const int nchunk = prm.nchunk;
     uint32_t it = 0;
 
     if (warp == XM_NCW) {
         // ------------------------------------------------------------------ producer warp
-        for (int64_t t = 0; t < ntiles; ++t) {
-            int64_t row0;
-            const int rows = tile_rows(t, row0);
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int64_t row0 = t * XM_MT;
+            const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
             // aligned shards have an even leading dimension, so a ragged last tile may copy one padding
             // row (rows rounded up to even: bulk copies move multiples of 16 bytes) and stay in bounds
             const bool bulk = prm.aligned != 0;
@@ -227,9 +209,9 @@ xmul_kernel(const XmulParams prm) {
         const int q = prm.q;
         const int64_t msz = prm.m * (int64_t)q;
         uint32_t tn = 0;
-        for (int64_t t = 0; t < ntiles; ++t, ++tn) {
-            int64_t row0;
-            const bool rok = r < tile_rows(t, row0);
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tn) {
+            const int64_t row0 = t * XM_MT;
+            const bool rok = row0 + r < prm.m;
             mbar_wait(tfull, tn & 1);
             for (int j0 = jh; j0 < q; j0 += 16) {
                 double pv[8];
@@ -265,10 +247,9 @@ xmul_kernel(const XmulParams prm) {
     uint32_t tn = 0;
     const int g = lane >> 2, kk = lane & 3;
     const int m0 = warp * 16;
-    for (int64_t t = 0; t < ntiles; ++t) {
-        int64_t row0;
-        const int rows = tile_rows(t, row0);
-        const bool active = m0 < rows;          // ragged last tile: warps without rows only keep the ring going
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * XM_MT;
+        const int rows = (int)min((int64_t)XM_MT, prm.m - row0);
         double acc[2][NPB][2];
         double ex[2][NEX > 0 ? NEX : 1];
 #pragma unroll
@@ -287,7 +268,6 @@ xmul_kernel(const XmulParams prm) {
                 const double* xs = reinterpret_cast<const double*>(stage_base + (size_t)buf * STAGE);
                 const double* ms = xs + XM_KC * XM_PITCH;
                 const double* mus = mu_s + ch * XM_KC;
-                if (active) {
 #pragma unroll
                 for (int k4 = 0; k4 < XM_KC / 4; ++k4) {
                     const int k = k4 * 4 + kk;
@@ -309,7 +289,6 @@ xmul_kernel(const XmulParams prm) {
                         ex[0][e] += a.x * b;
                         ex[1][e] += a.y * b;
                     }
-                }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[buf]);
@@ -436,8 +415,8 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     const int smem = nstage * stage + fixed;
     JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   smem));
-    // full waves of whole tiles + one ragged tile per CTA: every SM takes part as soon as there are 16 rows each
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((prm.m + 15) / 16, (int64_t)XM_OCC * c->num_sms));
+    const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)XM_OCC * c->num_sms);
     xmul_kernel<NPB, NEX, SWEEP, NCW><<<grid, XM_THREADS, smem, c->stream>>>(prm);
     JCB_LAUNCH_CHECK();
     return 0;
