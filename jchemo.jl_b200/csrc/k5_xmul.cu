@@ -425,13 +425,15 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
 // 256-row tiles (16 consumer warps) for narrow outputs without the sweep epilogue, else 128-row tiles
 template <int NPB, int NEX, bool SWEEP>
 static int launch_xmul_t(Ctx* c, XmulParams& prm) {
-    if constexpr (!SWEEP && NPB <= 4) {
-        static int wide = -1;
+    if constexpr (!SWEEP && NPB <= 7) {
+        static int wide = -1, wide_npb = 4;
         if (wide < 0) {
             const char* e = getenv("JCB_XM_WIDE");
             wide = e ? atoi(e) : 1;
+            const char* e2 = getenv("JCB_XM_WIDE_NPB");      // widest output (8-column blocks) the 256-row tile takes
+            wide_npb = e2 ? atoi(e2) : 4;
         }
-        if (wide && prm.m >= 256 * 148) {
+        if (wide && NPB <= wide_npb && prm.m >= 256 * 148) {
             const int r = launch_xmul_w<NPB, NEX, SWEEP, 16>(c, prm);
             if (r != -1000) return r;
         }
@@ -484,8 +486,13 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
     for (int c0 = 0; c0 < ncol_total; c0 += maxcol) {
         const int ncol = std::min(maxcol, ncol_total - c0);
         // full 8-column blocks by DMMA; 1-2 leftover columns by DFMA instead of a padded block
+        static int nex_max = -1;
+        if (nex_max < 0) {
+            const char* e = getenv("JCB_XM_NEX_MAX");        // leftover columns taken by DFMA (else a padded DMMA block)
+            nex_max = e ? atoi(e) : 2;
+        }
         int npb = ncol / 8, nex = ncol % 8;
-        if (npb == 0 || nex > 2) {
+        if (npb == 0 || nex > nex_max) {
             npb = (ncol + 7) / 8;
             nex = 0;
         }
