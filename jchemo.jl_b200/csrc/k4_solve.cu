@@ -954,6 +954,377 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
     cluster.sync();     // no CTA may exit while a peer can still store into its shared memory
 }
 
+// ----------------------------------------------------------------------------------------- K4, linear form
+// lvlin_kernel — the same 16-CTA cluster, but everything downstream of the eigenvector is LINEAR in it:
+//   w~ = XtY v,   r~ = w~ - R (P'w~) = Rho v   with  Rho  = XtY - R (P'XtY)         (p x q)
+//   zp~ = XtX r~ = Zeta v                      with  Zeta = XtX Rho                  (p x q)
+//   tt = r'zp = v'(Rho'Zeta) v / |w~|^2,  u = XtY'r = (XtY'Rho) v / |w~|,  |w~|^2 = v'M v,  M = XtY'XtY
+// so Rho, Zeta and the two small q x q products do not need v: fifteen warps build them WHILE warp 0 runs the
+// eigenvector iteration (half of an LV's critical path in lvdist_kernel), and three exchanges per LV
+// (A: partial M and Z = XtY'P;  G: all-gather of the Rho slices;  D: partial Rho'Zeta and XtY'Rho) replace four
+// that all sat behind v.  The q matvecs with XtX cost 10x the flops of the one they replace and are still off the
+// critical path.  An extra column e_1 rides along with XtY's q columns: when XtY has deflated to zero (v'Mv = 0;
+// LAPACK's svd of a zero matrix gives U = I, plskern.jl:154) the LV simply takes v = that column — the degenerate
+// case needs no code path of its own.  Used when its buffers fit in shared memory (p x (q+1) doubles for the
+// gathered Rho: p <= ~1800 at q = 10); lvdist_kernel otherwise.  Same determinism: every sum over CTAs runs in
+// rank order in every CTA, so all CTAs hold the same bits.
+constexpr int LVL_QAMAX = 18;            // q + 1 rounded up to even, q <= 16
+
+struct LvlLayout {
+    int pe, sp, qa, qp, nt, nta, lenA, lenD;
+    int rfull, xs, Ps, Rs, rho, zeta, zp, exA, exD, M, A, B, Z, Al, Be, v, c, sc, total;   // doubles
+};
+__host__ __device__ inline LvlLayout lvl_layout(int p, int q, int nlv, int per) {
+    LvlLayout L;
+    auto ev = [](int x) { return (x + 1) & ~1; };
+    L.pe = ev(p);
+    L.sp = per | 1;
+    L.qa = q + 1;
+    L.qp = ev(q + 1);
+    L.nt = q * (q + 1) / 2;
+    L.nta = L.qa * (L.qa + 1) / 2;
+    L.lenA = L.nt + L.qa * nlv;
+    L.lenD = L.nta + q * L.qa;
+    int o = 0;
+    L.rfull = o; o += L.pe * L.qp;          // first: 16-byte aligned rows for the double2 loads
+    L.xs = o; o += ev(L.qa * L.sp);
+    L.Ps = o; o += ev(nlv * L.sp);
+    L.Rs = o; o += ev(nlv * L.sp);
+    L.rho = o; o += ev(L.qa * L.sp);
+    L.zeta = o; o += ev(L.qa * L.sp);
+    L.zp = o; o += ev(L.sp);
+    L.exA = o; o += ev(LV16_CLUSTER * L.lenA);
+    L.exD = o; o += ev(LV16_CLUSTER * L.lenD);
+    L.M = o; o += ev(q * q);
+    L.A = o; o += ev(q * q);
+    L.B = o; o += ev(q * q);
+    L.Z = o; o += ev(L.qa * nlv);
+    L.Al = o; o += ev(L.nta);
+    L.Be = o; o += ev(q * L.qa);
+    L.v = o; o += ev(L.qa);
+    L.c = o; o += ev(q);
+    L.sc = o; o += 8;
+    L.total = o;
+    return L;
+}
+
+// one row of the XtX slice (held in registers: xr[u] = XtX[row][lane + 32 u]) against the gathered Rho: all 2*NJ2
+// columns at once, lanes over k, one butterfly per column at the end (every lane ends up with every sum)
+template <int NJ2, int KU>
+__device__ __forceinline__ void zeta_row(const double (&xr)[KU], const double* __restrict__ rfull, int qp, int p,
+                                         int lane, double (&out)[2 * NJ2]) {
+    double acc[2 * NJ2];
+#pragma unroll
+    for (int j = 0; j < 2 * NJ2; ++j) acc[j] = 0.0;
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+        const int k = lane + 32 * u;
+        if (k < p) {
+            const double2* rk = reinterpret_cast<const double2*>(rfull + (int64_t)k * qp);
+#pragma unroll
+            for (int j2 = 0; j2 < NJ2; ++j2) {
+                const double2 r = rk[j2];
+                acc[2 * j2] += xr[u] * r.x;
+                acc[2 * j2 + 1] += xr[u] * r.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * NJ2; ++j) out[j] = warp_sum(acc[j]);
+}
+
+template <int NJ2>
+__device__ __forceinline__ void zeta_rows(const double* __restrict__ XtX, int64_t P64, int lo, int nsl, int p,
+                                          const double* __restrict__ rfull, int qp, int qa, int sp,
+                                          double* __restrict__ zeta_s, uint64_t* barG, uint32_t par, int gwarp,
+                                          int ngw, int lane) {
+    constexpr int KU = 16;                // 32 * 16 = 512 columns per register pass
+    // rows gwarp, gwarp + ngw, ... of the slice.  The first row's XtX values are requested BEFORE the wait for
+    // the gathered Rho, so their L2 latency hides behind the exchange; later rows behind the previous row's FMAs.
+    double xr[KU];
+    int i = gwarp;
+    const int npass = (p + 32 * KU - 1) / (32 * KU);
+    auto load = [&](int row, int pass) {
+        const double* g = XtX + (int64_t)(lo + row) * P64 + pass * 32 * KU;
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            const int k = pass * 32 * KU + lane + 32 * u;
+            xr[u] = (row < nsl && k < p) ? __ldcg(g + lane + 32 * u) : 0.0;
+        }
+    };
+    load(i, 0);
+    mbar_wait(barG, par);
+    for (; i < nsl; i += ngw) {
+        double tot[2 * NJ2];
+#pragma unroll
+        for (int j = 0; j < 2 * NJ2; ++j) tot[j] = 0.0;
+        for (int pass = 0; pass < npass; ++pass) {
+            if (pass > 0) load(i, pass);
+            double out[2 * NJ2];
+            zeta_row<NJ2, KU>(xr, rfull + (int64_t)pass * 32 * KU * qp, qp, p - pass * 32 * KU, lane, out);
+#pragma unroll
+            for (int j = 0; j < 2 * NJ2; ++j) tot[j] += out[j];
+            if (pass + 1 == npass && i + ngw < nsl) load(i + ngw, 0);      // next row while this one is stored
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * NJ2; ++j)
+            if (j < qa && lane == (j & 31)) zeta_s[j * sp + i] = tot[j];
+    }
+}
+
+__global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm) {
+    if (prm.status[0] != 0.0) return;          // non-finite input: every CTA leaves before the first barrier
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) uint64_t bars[3];          // A (M, Z), G (Rho gather), D (Rho'Zeta, XtY'Rho)
+    const int p = prm.p, q = prm.q, nlv = prm.nlv;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster.block_rank();
+    constexpr int ncta = LV16_CLUSTER;
+    const int per = (p + ncta - 1) / ncta;
+    const int lo = min(p, rank * per), hi = min(p, lo + per), nsl = hi - lo;
+    const LvlLayout L = lvl_layout(p, q, nlv, per);
+    const int sp = L.sp, qa = L.qa, qp = L.qp, nt = L.nt, nta = L.nta, lenA = L.lenA, lenD = L.lenD;
+    double* rfull = sm + L.rfull;
+    double* xs = sm + L.xs;
+    double* Ps = sm + L.Ps;
+    double* Rs = sm + L.Rs;
+    double* rho_s = sm + L.rho;
+    double* zeta_s = sm + L.zeta;
+    double* zp_s = sm + L.zp;
+    double* exA = sm + L.exA;
+    double* exD = sm + L.exD;
+    double* M_s = sm + L.M;
+    double* A_s = sm + L.A;
+    double* B_s = sm + L.B;
+    double* Z_s = sm + L.Z;
+    double* Al_s = sm + L.Al;
+    double* Be_s = sm + L.Be;
+    double* v_s = sm + L.v;
+    double* c_s = sm + L.c;
+    double* sc_s = sm + L.sc;
+    const int64_t P64 = p;
+    const uint32_t barA = smem_u32(&bars[0]), barG = smem_u32(&bars[1]), barD = smem_u32(&bars[2]);
+    const uint32_t bytesG = (uint32_t)(p * qa * 8), bytesD = (uint32_t)(ncta * lenD * 8);
+
+    if (tid == 0) {
+        for (int b = 0; b < 3; ++b) mbar_init(&bars[b], 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)(ncta * nt * 8));      // LV 0: M only (Z has no column yet)
+        mbar_arrive_expect_tx(&bars[1], bytesG);
+        mbar_arrive_expect_tx(&bars[2], bytesD);
+    }
+    for (int e = tid; e < nsl * q; e += LV_THREADS) {
+        const int j = e / nsl, i = e - j * nsl;
+        xs[j * sp + i] = prm.XtY[lo + i + (int64_t)j * P64];
+    }
+    for (int i = tid; i < nsl; i += LV_THREADS) xs[q * sp + i] = (lo + i == 0) ? 1.0 : 0.0;     // the e_1 column
+    // triangle index -> (i <= j) for the M entries (nt <= 136 < LV_THREADS)
+    int ti = 0, tj = 0;
+    if (tid < nt) {
+        int rem = tid;
+        while (rem >= q - ti) { rem -= q - ti; ++ti; }
+        tj = ti + rem;
+    }
+    __syncthreads();
+    cluster.sync();     // every CTA is running and its barriers are initialised before the first remote store
+
+    constexpr int NGT = LV_THREADS - 32;        // threads of warps 1..15
+    for (int a = 0; a < nlv; ++a) {
+        const uint32_t par = a & 1;
+        const bool more = a + 1 < nlv;
+        const int nA = nt + qa * a;
+        // ---------------------------------------------------------------- 1: partial M, Z -> slot [rank] everywhere
+        for (int e = tid; e < nA; e += LV_THREADS) {
+            const double* ci;
+            const double* cj;
+            if (e < nt) {
+                ci = xs + ti * sp;
+                cj = xs + tj * sp;
+            } else {
+                const int f = e - nt, j = f / qa, i = f - j * qa;
+                ci = xs + i * sp;
+                cj = Ps + j * sp;
+            }
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for (; k + 3 < nsl; k += 4) {
+                s0 += ci[k] * cj[k];
+                s1 += ci[k + 1] * cj[k + 1];
+                s2 += ci[k + 2] * cj[k + 2];
+                s3 += ci[k + 3] * cj[k + 3];
+            }
+            for (; k < nsl; ++k) s0 += ci[k] * cj[k];
+            const double val = (s0 + s1) + (s2 + s3);
+            const uint32_t dst = smem_u32(exA + rank * lenA + e);
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barA, cta));
+        }
+        // ---------------------------------------------------------------- 2: sums in rank order -> M, Z
+        mbar_wait(&bars[0], par);
+        if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], (uint32_t)(ncta * (nt + qa * (a + 1)) * 8));
+        for (int e = tid; e < nA; e += LV_THREADS) {
+            double v[ncta];
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) v[cta] = exA[cta * lenA + e];
+            double s = 0.0;
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+            if (e < nt) {
+                M_s[ti * q + tj] = s;
+                M_s[tj * q + ti] = s;
+            } else {
+                Z_s[e - nt] = s;                    // Z_s[j * qa + i] = (column i of [XtY | e_1])' P_j
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // ------------------------------------------------------------ 3a: eigenvector (one warp)
+            if (q > 1) {
+                eig_dominant_warp_q(q, M_s, A_s, B_s, v_s, lane);
+            } else {
+                if (lane == 0) v_s[0] = 1.0;
+                __syncwarp();
+            }
+            double t = 0.0;
+            if (lane < q) {
+                double r = 0.0;
+                for (int j = 0; j < q; ++j) r += M_s[lane * q + j] * v_s[j];
+                t = r * v_s[lane];
+            }
+            t = warp_sum(t);                                    // |XtY v|^2 = v'M v
+            const bool degen = !(t > 0.0);
+            const double vl = (lane < q) ? v_s[lane] : 0.0;
+            __syncwarp();
+            if (lane <= q) v_s[lane] = degen ? (lane == q ? 1.0 : 0.0) : vl;      // degenerate: w = e_1
+            if (lane == 0) sc_s[0] = degen ? 1.0 : t;
+            __syncwarp();
+        } else {
+            // ------------------------------------------------------------ 3b: Rho, Zeta, small products (15 warps)
+            const int gt = tid - 32;
+            for (int idx = gt; idx < qa * nsl; idx += NGT) {
+                const int j = idx / nsl, i = idx - j * nsl;
+                double r0 = xs[j * sp + i], r1 = 0.0;
+                int l = 0;
+                for (; l + 1 < a; l += 2) {
+                    r0 -= Rs[l * sp + i] * Z_s[l * qa + j];
+                    r1 -= Rs[(l + 1) * sp + i] * Z_s[(l + 1) * qa + j];
+                }
+                if (l < a) r0 -= Rs[l * sp + i] * Z_s[l * qa + j];
+                const double val = r0 + r1;
+                rho_s[j * sp + i] = val;
+                const uint32_t dst = smem_u32(rfull + (int64_t)(lo + i) * qp + j);
+#pragma unroll
+                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barG, cta));
+            }
+            // Zeta slice = XtX[lo:hi, :] Rho (waits for the gathered Rho inside, after requesting its first row)
+            switch (qp / 2) {
+#define JCB_ZR(N) case N: zeta_rows<N>(prm.XtX, P64, lo, nsl, p, rfull, qp, qa, sp, zeta_s, &bars[1], par, warp - 1, 15, lane); break;
+                JCB_ZR(1) JCB_ZR(2) JCB_ZR(3) JCB_ZR(4) JCB_ZR(5) JCB_ZR(6) JCB_ZR(7) JCB_ZR(8) JCB_ZR(9)
+#undef JCB_ZR
+                default: break;
+            }
+            if (gt == 0 && more) mbar_arrive_expect_tx(&bars[1], bytesG);
+            asm volatile("bar.sync 1, %0;" ::"r"(NGT) : "memory");       // rho_s, zeta_s of every row are in place
+            for (int e = gt; e < lenD; e += NGT) {
+                const double* ci;
+                const double* cj;
+                if (e < nta) {                      // upper triangle of Rho'Zeta
+                    int i1 = 0, rem = e;
+                    while (rem >= qa - i1) { rem -= qa - i1; ++i1; }
+                    ci = rho_s + i1 * sp;
+                    cj = zeta_s + (i1 + rem) * sp;
+                } else {                            // XtY'Rho (q x qa)
+                    const int f = e - nta, j1 = f / qa, j2 = f - j1 * qa;
+                    ci = xs + j1 * sp;
+                    cj = rho_s + j2 * sp;
+                }
+                double s0 = 0.0, s1 = 0.0;
+                int k = 0;
+                for (; k + 1 < nsl; k += 2) {
+                    s0 += ci[k] * cj[k];
+                    s1 += ci[k + 1] * cj[k + 1];
+                }
+                if (k < nsl) s0 += ci[k] * cj[k];
+                const double val = s0 + s1;
+                const uint32_t dst = smem_u32(exD + rank * lenD + e);
+#pragma unroll
+                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barD, cta));
+            }
+        }
+        // ---------------------------------------------------------------- 4: sums in rank order -> Rho'Zeta, XtY'Rho
+        mbar_wait(&bars[2], par);
+        if (tid == 0 && more) mbar_arrive_expect_tx(&bars[2], bytesD);
+        for (int e = tid; e < lenD; e += LV_THREADS) {
+            double v[ncta];
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) v[cta] = exD[cta * lenD + e];
+            double s = 0.0;
+#pragma unroll
+            for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+            if (e < nta) Al_s[e] = s;
+            else Be_s[e - nta] = s;
+        }
+        __syncthreads();                 // also publishes v and |w~|^2 of warp 0
+        // ---------------------------------------------------------------- 5: tt, c (one warp, same in every CTA)
+        if (warp == 0) {
+            const double nrm2 = sc_s[0], nrm = sqrt(nrm2);
+            double t = 0.0;
+            for (int e = lane; e < nta; e += 32) {
+                int i1 = 0, rem = e;
+                while (rem >= qa - i1) { rem -= qa - i1; ++i1; }
+                const int i2 = i1 + rem;
+                t += Al_s[e] * v_s[i1] * v_s[i2] * (i1 == i2 ? 1.0 : 2.0);
+            }
+            const double tt = warp_sum(t) / nrm2;
+            // tt == 0 (r = 0: more LVs asked than the data carry): the reference divides 0/0; here the LV is inert
+            if (lane < q) {
+                double u = 0.0;
+                for (int i = 0; i < qa; ++i) u += Be_s[lane * qa + i] * v_s[i];
+                const double cv = tt > 0.0 ? (u / nrm) / tt : 0.0;
+                c_s[lane] = cv;
+                if (rank == 0) prm.C[lane + (int64_t)a * q] = cv;
+            }
+            if (lane == 0) {
+                sc_s[1] = tt;
+                sc_s[2] = nrm;
+                if (rank == 0) prm.TT[a] = tt;
+            }
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- 6: this CTA's slices of w, r, zp; deflate
+        {
+            const double tt = sc_s[1], nrm = sc_s[2];
+            if (tid < nsl) {
+                double wv = 0.0, rv = 0.0, zv = 0.0;
+                for (int j = 0; j < qa; ++j) {
+                    const double vj = v_s[j];
+                    wv += xs[j * sp + tid] * vj;
+                    rv += rho_s[j * sp + tid] * vj;
+                    zv += zeta_s[j * sp + tid] * vj;
+                }
+                wv /= nrm;
+                rv /= nrm;
+                zv /= nrm;
+                const double pv = tt > 0.0 ? zv / tt : 0.0;
+                zp_s[tid] = zv;
+                Ps[a * sp + tid] = pv;
+                Rs[a * sp + tid] = rv;
+                prm.P[lo + tid + (int64_t)a * P64] = pv;
+                prm.R[lo + tid + (int64_t)a * P64] = rv;
+                prm.W[lo + tid + (int64_t)a * P64] = wv;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nsl * q; e += LV_THREADS) {
+            const int j = e / nsl, i = e - j * nsl;
+            xs[j * sp + i] -= zp_s[i] * c_s[j];
+        }
+        __syncthreads();
+    }
+    cluster.sync();     // no CTA may exit while a peer can still store into its shared memory
+}
+
 #ifdef JCB_K1_TRACE
 static long long* g_lv_trace = nullptr;
 extern "C" int jcb200_debug_lv_trace(long long* host) {
@@ -1029,6 +1400,44 @@ int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_
     static int lv16_ok = -1;             // -1: not probed; 0: no 16-CTA cluster on this device
     const bool force8 = getenv("JCB_LV_CLUSTER8") != nullptr;
     const int per = (int)((p + LV16_CLUSTER - 1) / LV16_CLUSTER);
+    // linear form (everything after the eigenvector is a q-term combination: Rho, Zeta built beside the
+    // eigenvector iteration) when its buffers fit; JCB_LV_LINEAR=0 keeps the four-exchange form
+    {
+        const char* e = getenv("JCB_LV_LINEAR");
+        const bool want = !(e && atoi(e) == 0);
+        const size_t smem_lin = (size_t)lvl_layout((int)p, (int)q, nlv, per).total * 8;
+        if (want && q <= 16 && per <= LV_THREADS && lv16_ok != 0 && !force8 && smem_lin <= 227 * 1024 - 64) {
+            JCB_CUDA(cudaFuncSetAttribute(lvlin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
+            JCB_CUDA(cudaFuncSetAttribute(lvlin_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(LV16_CLUSTER);
+            cfg.blockDim = dim3(LV_THREADS);
+            cfg.dynamicSmemBytes = smem_lin;
+            cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = LV16_CLUSTER;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            static int lin_ok = -1;
+            if (lin_ok < 0) {
+                int ncl = 0;
+                const cudaError_t ce = cudaOccupancyMaxActiveClusters(&ncl, lvlin_kernel, &cfg);
+                if (ce != cudaSuccess) (void)cudaGetLastError();
+                lin_ok = (ce == cudaSuccess && ncl >= 1) ? 1 : 0;
+            }
+            if (lin_ok == 1) {
+                prm.xty_smem = 1;
+                phase_begin(c, JCB200_T_LVLOOP);
+                JCB_CUDA(cudaLaunchKernelEx(&cfg, lvlin_kernel, prm));
+                JCB_LAUNCH_CHECK();
+                phase_end(c, JCB200_T_LVLOOP);
+                return 0;
+            }
+        }
+    }
     if (q <= 16 && per <= LV_THREADS && nlv <= LV_THREADS && lv16_ok != 0 && !force8) {
         const size_t max_smem = 227 * 1024 - 64;      // the kernel also holds five mbarriers statically
         const size_t sm_gs = (size_t)lvd_layout((int)p, (int)q, nlv, per, true).total * 8;

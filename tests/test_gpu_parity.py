@@ -439,10 +439,12 @@ def test_locwlv_neighbourhood_sizes(jc):
     (2500, 610, 1, 12, False),   # q = 1, shared-memory slice at its size limit
     (1500, 100, 4, 90, False),   # nlv > 64: several rounds of the dot exchange
 ])
-def test_lvloop_forms(jc, n, p, q, nlv, scal):
-    """Every form of the LV-loop kernel (distributed 16-CTA cluster with the XtX slice in shared memory or
-    in L2; portable 8-CTA fallback) against the oracle, on data with a real X-Y relation so that every
-    requested LV is well determined."""
+@pytest.mark.parametrize("linear", [True, False])
+def test_lvloop_forms(jc, n, p, q, nlv, scal, linear, monkeypatch):
+    """Every form of the LV-loop kernel (the linear form that builds Rho / Zeta beside the eigenvector iteration;
+    the four-exchange 16-CTA cluster form with the XtX slice in shared memory or in L2; the portable 8-CTA
+    fallback) against the oracle, on data with a real X-Y relation so that every requested LV is well determined."""
+    monkeypatch.setenv("JCB_LV_LINEAR", "1" if linear else "0")
     rng = np.random.default_rng(7)
     X = synth.synth_matrix(1, n, p)
     B = rng.standard_normal((p, q))
