@@ -622,6 +622,17 @@ __device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t 
                  : "memory");
 }
 
+// bulk copy of a contiguous block of this CTA's shared memory into a peer CTA's shared memory; completes `bytes`
+// tx-bytes on the PEER's mbarrier.  ONE instruction per (block, destination) where st.async needs one per double:
+// 13 700 st.async per LV made the first version of lvlin_kernel three times slower than lvdist_kernel.
+// bytes: multiple of 16; both addresses 16-byte aligned; the source must have been fenced to the async proxy.
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+
 template <bool GS>
 __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams prm) {
     if (prm.status[0] != 0.0) return;          // non-finite input: every CTA leaves before the first barrier
@@ -983,8 +994,8 @@ __host__ __device__ inline LvlLayout lvl_layout(int p, int q, int nlv, int per) 
     L.qp = ev(q + 1);
     L.nt = q * (q + 1) / 2;
     L.nta = L.qa * (L.qa + 1) / 2;
-    L.lenA = L.nt + L.qa * nlv;
-    L.lenD = L.nta + q * L.qa;
+    L.lenA = ev(L.nt + L.qa * nlv);       // even: slots stay 16-byte aligned for the bulk copies
+    L.lenD = ev(L.nta + q * L.qa);
     int o = 0;
     L.rfull = o; o += L.pe * L.qp;          // first: 16-byte aligned rows for the double2 loads
     L.xs = o; o += ev(L.qa * L.sp);
@@ -1007,6 +1018,8 @@ __host__ __device__ inline LvlLayout lvl_layout(int p, int q, int nlv, int per) 
     L.total = o;
     return L;
 }
+
+__host__ __device__ inline int pe_qp_pad(const LvlLayout& L) { return L.pe * L.qp; }
 
 // one row of the XtX slice (held in registers: xr[u] = XtX[row][lane + 32 u]) against the gathered Rho: all 2*NJ2
 // columns at once, lanes over k, one butterfly per column at the end (every lane ends up with every sum)
@@ -1105,15 +1118,18 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
     double* sc_s = sm + L.sc;
     const int64_t P64 = p;
     const uint32_t barA = smem_u32(&bars[0]), barG = smem_u32(&bars[1]), barD = smem_u32(&bars[2]);
-    const uint32_t bytesG = (uint32_t)(p * qa * 8), bytesD = (uint32_t)(ncta * lenD * 8);
+    // every exchange: a CTA writes its own part in place and bulk-copies it to the 15 peers
+    auto evn = [](int x) { return (x + 1) & ~1; };
+    const uint32_t bytesG = (uint32_t)((p - nsl) * qp * 8), bytesD = (uint32_t)((ncta - 1) * lenD * 8);
 
     if (tid == 0) {
         for (int b = 0; b < 3; ++b) mbar_init(&bars[b], 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&bars[0], (uint32_t)(ncta * nt * 8));      // LV 0: M only (Z has no column yet)
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)((ncta - 1) * evn(nt) * 8));   // LV 0: M only (Z has no column yet)
         mbar_arrive_expect_tx(&bars[1], bytesG);
         mbar_arrive_expect_tx(&bars[2], bytesD);
     }
+    for (int e = tid; e < pe_qp_pad(L); e += LV_THREADS) rfull[e] = 0.0;     // pad column of Rho stays zero
     for (int e = tid; e < nsl * q; e += LV_THREADS) {
         const int j = e / nsl, i = e - j * nsl;
         xs[j * sp + i] = prm.XtY[lo + i + (int64_t)j * P64];
@@ -1155,14 +1171,17 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
                 s3 += ci[k + 3] * cj[k + 3];
             }
             for (; k < nsl; ++k) s0 += ci[k] * cj[k];
-            const double val = (s0 + s1) + (s2 + s3);
-            const uint32_t dst = smem_u32(exA + rank * lenA + e);
-#pragma unroll
-            for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barA, cta));
+            exA[rank * lenA + e] = (s0 + s1) + (s2 + s3);          // own slot, in place
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid < ncta && tid != rank) {
+            const uint32_t src = smem_u32(exA + rank * lenA);
+            bulk_s2c(mapa_u32(src, tid), src, (uint32_t)(evn(nA) * 8), mapa_u32(barA, tid));
         }
         // ---------------------------------------------------------------- 2: sums in rank order -> M, Z
         mbar_wait(&bars[0], par);
-        if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], (uint32_t)(ncta * (nt + qa * (a + 1)) * 8));
+        if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], (uint32_t)((ncta - 1) * evn(nt + qa * (a + 1)) * 8));
         for (int e = tid; e < nA; e += LV_THREADS) {
             double v[ncta];
 #pragma unroll
@@ -1213,9 +1232,13 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
                 if (l < a) r0 -= Rs[l * sp + i] * Z_s[l * qa + j];
                 const double val = r0 + r1;
                 rho_s[j * sp + i] = val;
-                const uint32_t dst = smem_u32(rfull + (int64_t)(lo + i) * qp + j);
-#pragma unroll
-                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barG, cta));
+                rfull[(int64_t)(lo + i) * qp + j] = val;                // own rows of the gathered Rho, in place
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"r"(NGT) : "memory");
+            if (gt < ncta && gt != rank && nsl > 0) {
+                const uint32_t src = smem_u32(rfull + (int64_t)lo * qp);
+                bulk_s2c(mapa_u32(src, gt), src, (uint32_t)(nsl * qp * 8), mapa_u32(barG, gt));
             }
             // Zeta slice = XtX[lo:hi, :] Rho (waits for the gathered Rho inside, after requesting its first row)
             switch (qp / 2) {
@@ -1226,7 +1249,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             }
             if (gt == 0 && more) mbar_arrive_expect_tx(&bars[1], bytesG);
             asm volatile("bar.sync 1, %0;" ::"r"(NGT) : "memory");       // rho_s, zeta_s of every row are in place
-            for (int e = gt; e < lenD; e += NGT) {
+            for (int e = gt; e < nta + q * qa; e += NGT) {
                 const double* ci;
                 const double* cj;
                 if (e < nta) {                      // upper triangle of Rho'Zeta
@@ -1246,16 +1269,19 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
                     s1 += ci[k + 1] * cj[k + 1];
                 }
                 if (k < nsl) s0 += ci[k] * cj[k];
-                const double val = s0 + s1;
-                const uint32_t dst = smem_u32(exD + rank * lenD + e);
-#pragma unroll
-                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barD, cta));
+                exD[rank * lenD + e] = s0 + s1;                         // own slot, in place
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"r"(NGT) : "memory");
+            if (gt < ncta && gt != rank) {
+                const uint32_t src = smem_u32(exD + rank * lenD);
+                bulk_s2c(mapa_u32(src, gt), src, (uint32_t)(lenD * 8), mapa_u32(barD, gt));
             }
         }
         // ---------------------------------------------------------------- 4: sums in rank order -> Rho'Zeta, XtY'Rho
         mbar_wait(&bars[2], par);
         if (tid == 0 && more) mbar_arrive_expect_tx(&bars[2], bytesD);
-        for (int e = tid; e < lenD; e += LV_THREADS) {
+        for (int e = tid; e < nta + q * qa; e += LV_THREADS) {
             double v[ncta];
 #pragma unroll
             for (int cta = 0; cta < ncta; ++cta) v[cta] = exD[cta * lenD + e];
