@@ -174,6 +174,21 @@ struct LvParams {
 #else
 #define LV_MARK(idx) do { } while (0)
 #endif
+// lvlin_kernel: thread 0 (the eigenvector warp) accumulates into trace[0..7], thread 32 (first of the fifteen
+// builder warps) into trace[8..15]
+#ifdef JCB_K1_TRACE
+#define LVL_MARK(idx)                                                                          \
+    do {                                                                                       \
+        if (rank == 0 && (tid == 0 || tid == 32) && prm.trace) {                               \
+            const long long _t = clock64();                                                    \
+            atomicAdd((unsigned long long*)&prm.trace[(tid == 0 ? 0 : 8) + (idx)],             \
+                      (unsigned long long)(_t - lmark));                                       \
+            lmark = _t;                                                                        \
+        }                                                                                      \
+    } while (0)
+#else
+#define LVL_MARK(idx) do { } while (0)
+#endif
 
 // dot of a shared vector with a global column, lanes strided, 8 independent loads in flight.  The
 // ragged last chunk is PREDICATED, not peeled: a peeled remainder loop splits the warp (p = 500: lanes
@@ -1050,7 +1065,7 @@ template <int NJ2>
 __device__ __forceinline__ void zeta_rows(const double* __restrict__ XtX, int64_t P64, int lo, int nsl, int p,
                                           const double* __restrict__ rfull, int qp, int qa, int sp,
                                           double* __restrict__ zeta_s, uint64_t* barG, uint32_t par, int gwarp,
-                                          int ngw, int lane) {
+                                          int ngw, int lane, long long* tr) {
     constexpr int KU = 16;                // 32 * 16 = 512 columns per register pass
     // rows gwarp, gwarp + ngw, ... of the slice.  The first row's XtX values are requested BEFORE the wait for
     // the gathered Rho, so their L2 latency hides behind the exchange; later rows behind the previous row's FMAs.
@@ -1065,8 +1080,14 @@ __device__ __forceinline__ void zeta_rows(const double* __restrict__ XtX, int64_
             xr[u] = (row < nsl && k < p) ? __ldcg(g + lane + 32 * u) : 0.0;
         }
     };
+    long long t0 = tr ? clock64() : 0;
     load(i, 0);
     mbar_wait(barG, par);
+    if (tr) {      // debug builds: [16] request of the first row + wait for the gathered Rho, [17] the rows themselves
+        const long long t1 = clock64();
+        atomicAdd((unsigned long long*)&tr[16], (unsigned long long)(t1 - t0));
+        t0 = t1;
+    }
     for (; i < nsl; i += ngw) {
         double tot[2 * NJ2];
 #pragma unroll
@@ -1083,6 +1104,7 @@ __device__ __forceinline__ void zeta_rows(const double* __restrict__ XtX, int64_
         for (int j = 0; j < 2 * NJ2; ++j)
             if (j < qa && lane == (j & 31)) zeta_s[j * sp + i] = tot[j];
     }
+    if (tr) atomicAdd((unsigned long long*)&tr[17], (unsigned long long)(clock64() - t0));
 }
 
 __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm) {
@@ -1146,10 +1168,14 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
     cluster.sync();     // every CTA is running and its barriers are initialised before the first remote store
 
     constexpr int NGT = LV_THREADS - 32;        // threads of warps 1..15
+#ifdef JCB_K1_TRACE
+    long long lmark = clock64();
+#endif
     for (int a = 0; a < nlv; ++a) {
         const uint32_t par = a & 1;
         const bool more = a + 1 < nlv;
         const int nA = nt + qa * a;
+        LVL_MARK(7);
         // ---------------------------------------------------------------- 1: partial M, Z -> slot [rank] everywhere
         for (int e = tid; e < nA; e += LV_THREADS) {
             const double* ci;
@@ -1179,8 +1205,10 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             const uint32_t src = smem_u32(exA + rank * lenA);
             bulk_s2c(mapa_u32(src, tid), src, (uint32_t)(evn(nA) * 8), mapa_u32(barA, tid));
         }
+        LVL_MARK(0);                     // partial M, Z + send
         // ---------------------------------------------------------------- 2: sums in rank order -> M, Z
         mbar_wait(&bars[0], par);
+        LVL_MARK(1);                     // wait A
         if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], (uint32_t)((ncta - 1) * evn(nt + qa * (a + 1)) * 8));
         for (int e = tid; e < nA; e += LV_THREADS) {
             double v[ncta];
@@ -1197,6 +1225,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             }
         }
         __syncthreads();
+        LVL_MARK(2);                     // sum A + sync
         if (warp == 0) {
             // ------------------------------------------------------------ 3a: eigenvector (one warp)
             if (q > 1) {
@@ -1218,6 +1247,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             if (lane <= q) v_s[lane] = degen ? (lane == q ? 1.0 : 0.0) : vl;      // degenerate: w = e_1
             if (lane == 0) sc_s[0] = degen ? 1.0 : t;
             __syncwarp();
+            LVL_MARK(3);                 // thread 0: eigenvector
         } else {
             // ------------------------------------------------------------ 3b: Rho, Zeta, small products (15 warps)
             const int gt = tid - 32;
@@ -1240,15 +1270,23 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
                 const uint32_t src = smem_u32(rfull + (int64_t)lo * qp);
                 bulk_s2c(mapa_u32(src, gt), src, (uint32_t)(nsl * qp * 8), mapa_u32(barG, gt));
             }
+            LVL_MARK(3);                 // thread 32: Rho + send
             // Zeta slice = XtX[lo:hi, :] Rho (waits for the gathered Rho inside, after requesting its first row)
+#ifdef JCB_K1_TRACE
+            long long* ztr = (rank == 0 && tid == 32) ? prm.trace : nullptr;
+#else
+            long long* ztr = nullptr;
+#endif
             switch (qp / 2) {
-#define JCB_ZR(N) case N: zeta_rows<N>(prm.XtX, P64, lo, nsl, p, rfull, qp, qa, sp, zeta_s, &bars[1], par, warp - 1, 15, lane); break;
+#define JCB_ZR(N) case N: zeta_rows<N>(prm.XtX, P64, lo, nsl, p, rfull, qp, qa, sp, zeta_s, &bars[1], par, warp - 1, 15, lane, ztr); break;
                 JCB_ZR(1) JCB_ZR(2) JCB_ZR(3) JCB_ZR(4) JCB_ZR(5) JCB_ZR(6) JCB_ZR(7) JCB_ZR(8) JCB_ZR(9)
 #undef JCB_ZR
                 default: break;
             }
+            LVL_MARK(4);                 // thread 32: wait G + Zeta rows of warp 1
             if (gt == 0 && more) mbar_arrive_expect_tx(&bars[1], bytesG);
             asm volatile("bar.sync 1, %0;" ::"r"(NGT) : "memory");       // rho_s, zeta_s of every row are in place
+            LVL_MARK(5);                 // thread 32: barrier after Zeta (slowest builder warp)
             for (int e = gt; e < nta + q * qa; e += NGT) {
                 const double* ci;
                 const double* cj;
@@ -1277,9 +1315,11 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
                 const uint32_t src = smem_u32(exD + rank * lenD);
                 bulk_s2c(mapa_u32(src, gt), src, (uint32_t)(lenD * 8), mapa_u32(barD, gt));
             }
+            LVL_MARK(6);                 // thread 32: small products + send
         }
         // ---------------------------------------------------------------- 4: sums in rank order -> Rho'Zeta, XtY'Rho
         mbar_wait(&bars[2], par);
+        LVL_MARK(4 + (tid == 0 ? 0 : 3));        // thread 0: [4] wait D (= the builders' branch); thread 32: [7'] wait D
         if (tid == 0 && more) mbar_arrive_expect_tx(&bars[2], bytesD);
         for (int e = tid; e < nta + q * qa; e += LV_THREADS) {
             double v[ncta];
@@ -1292,6 +1332,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             else Be_s[e - nta] = s;
         }
         __syncthreads();                 // also publishes v and |w~|^2 of warp 0
+        LVL_MARK(5);                     // thread 0: sum D + sync
         // ---------------------------------------------------------------- 5: tt, c (one warp, same in every CTA)
         if (warp == 0) {
             const double nrm2 = sc_s[0], nrm = sqrt(nrm2);
@@ -1347,6 +1388,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvlin_kernel(const LvParams prm
             xs[j * sp + i] -= zp_s[i] * c_s[j];
         }
         __syncthreads();
+        LVL_MARK(6);                     // thread 0: tt, c, slices, deflate
     }
     cluster.sync();     // no CTA may exit while a peer can still store into its shared memory
 }
@@ -1356,8 +1398,8 @@ static long long* g_lv_trace = nullptr;
 extern "C" int jcb200_debug_lv_trace(long long* host) {
     if (!g_lv_trace) return -1;
     cudaDeviceSynchronize();
-    cudaMemcpy(host, g_lv_trace, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
-    return 16;
+    cudaMemcpy(host, g_lv_trace, 24 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return 24;
 }
 #endif
 
@@ -1416,8 +1458,8 @@ int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_
 #ifdef JCB_K1_TRACE
     {
         static long long* tb = nullptr;
-        if (!tb) cudaMalloc(&tb, 16 * sizeof(long long));
-        cudaMemsetAsync(tb, 0, 16 * sizeof(long long), c->stream);
+        if (!tb) cudaMalloc(&tb, 24 * sizeof(long long));
+        cudaMemsetAsync(tb, 0, 24 * sizeof(long long), c->stream);
         prm.trace = tb;
         g_lv_trace = tb;
     }
@@ -1427,10 +1469,14 @@ int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_
     const bool force8 = getenv("JCB_LV_CLUSTER8") != nullptr;
     const int per = (int)((p + LV16_CLUSTER - 1) / LV16_CLUSTER);
     // linear form (everything after the eigenvector is a q-term combination: Rho, Zeta built beside the
-    // eigenvector iteration) when its buffers fit; JCB_LV_LINEAR=0 keeps the four-exchange form
+    // eigenvector iteration), OPT-IN with JCB_LV_LINEAR=1: correct on every test shape but measured SLOWER than the
+    // four-exchange form at C2 (0.68 vs 0.27 ms; per-phase clock64 trace in profiles/lv_trace_r02.txt): the q + 1
+    // matvecs read the gathered Rho from shared memory once per row (1.5 MB per LV at 128 B/clk), the eigenvector
+    // warp runs 3.4x slower beside fifteen DFMA-heavy warps, and every exchange costs ~2 K cycles whatever it
+    // carries.  Kept as the starting point for a k-split Zeta (lane = row, XtX read by symmetry, Rho broadcast).
     {
         const char* e = getenv("JCB_LV_LINEAR");
-        const bool want = !(e && atoi(e) == 0);
+        const bool want = e && atoi(e) != 0;
         const size_t smem_lin = (size_t)lvl_layout((int)p, (int)q, nlv, per).total * 8;
         if (want && q <= 16 && per <= LV_THREADS && lv16_ok != 0 && !force8 && smem_lin <= 227 * 1024 - 64) {
             JCB_CUDA(cudaFuncSetAttribute(lvlin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
