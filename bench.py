@@ -323,8 +323,7 @@ def main():
     n_glob = args.rows
     lo, hi = sharded.shard_rows(n_glob, rank, world)
     n_loc = hi - lo
-    X = dev.colmajor_empty(max(n_loc, 2), P, device)
-    Y = dev.colmajor_empty(max(n_loc, 2), Q, device)
+    X, Y = dev.colmajor_empty_xy(max(n_loc, 2), P, Q, device)      # Y behind X: one n x (p + q) matrix for K1
     if n_loc > 0:
         dev.fill_uniform(X, n_loc, 1, lo, n_glob)
         dev.fill_uniform(Y, n_loc, 2, lo, n_glob)
@@ -388,8 +387,7 @@ def main():
     if world > 1 and extras and n_glob == N_GLOBAL:
         del X, Y, model
         nw = N_GLOBAL
-        Xw = dev.colmajor_empty(nw, P, device)
-        Yw = dev.colmajor_empty(nw, Q, device)
+        Xw, Yw = dev.colmajor_empty_xy(nw, P, Q, device)
         dev.fill_uniform(Xw, nw, 1, rank * nw, nw * world)
         dev.fill_uniform(Yw, nw, 2, rank * nw, nw * world)
         mw = dev.DeviceModel(nw, P, Q, NLV, device)
@@ -480,8 +478,7 @@ def golden_parity(np, torch, dist, dev, sharded, rank, world, device, comm):
     n, p, q, nlv = 20000, 500, 10, 25
     lo, hi = sharded.shard_rows(n, rank, world)
     nl = hi - lo
-    Xg = dev.colmajor_empty(max(nl, 2), p, device)
-    Yg = dev.colmajor_empty(max(nl, 2), q, device)
+    Xg, Yg = dev.colmajor_empty_xy(max(nl, 2), p, q, device)
     if nl > 0:
         dev.fill_uniform(Xg, nl, 1, lo, n)
         dev.fill_uniform(Yg, nl, 2, lo, n)
@@ -542,8 +539,7 @@ def c4_leg(torch, dist, dev, sharded, _lib, rank, world, device, use_comm, comm,
     dist.all_reduce(fits, op=dist.ReduceOp.MIN)
     if fits.item() == 0.0:
         return {"skipped": f"rank shard needs {need * 1e-9:.0f} GB, {free * 1e-9:.0f} GB free"}
-    X = dev.colmajor_empty(nl, p, device)
-    Y = dev.colmajor_empty(nl, q, device)
+    X, Y = dev.colmajor_empty_xy(nl, p, q, device)
     dev.fill_uniform(X, nl, 1, lo, n)
     dev.fill_uniform(Y, nl, 2, lo, n)
     model = dev.DeviceModel(nl, p, q, nlv, device)

@@ -17,7 +17,7 @@ torch.cuda.set_device(0); dev.init(0); dev.use_current_stream()
 out = {}
 for N in (1, 2, 4, 8):
     nl = a.n // N
-    X = dev.colmajor_empty(nl, a.p); Y = dev.colmajor_empty(nl, a.q)
+    X, Y = dev.colmajor_empty_xy(nl, a.p, a.q) if os.environ.get("JCB_XY", "1") != "0" else (dev.colmajor_empty(nl, a.p), dev.colmajor_empty(nl, a.q))
     dev.fill_uniform(X, nl, 1, 0, a.n); dev.fill_uniform(Y, nl, 2, 0, a.n)
     model = dev.DeviceModel(nl, a.p, a.q, a.nlv)
     pivot = torch.empty(a.p + a.q + 1, dtype=torch.float64, device="cuda")

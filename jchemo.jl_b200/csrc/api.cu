@@ -343,15 +343,14 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         s.r0 = std::min(n, (int64_t)d * per);
         s.nr = std::min(per, n - s.r0);
         s.ld = even_up(std::max<int64_t>(s.nr, 2));
-        JCB_TRY(ensure(c->hX, (size_t)s.ld * p * 8));
-        JCB_TRY(ensure(c->hY, (size_t)s.ld * q * 8));
+        JCB_TRY(ensure(c->hX, (size_t)s.ld * (p + q) * 8));      // [X | Y] in one buffer: joint column space in K1
         JCB_TRY(ensure(c->hW, (size_t)s.ld * 2 * 8));
         JCB_TRY(ensure(c->hT, (size_t)s.ld * (nlv > 0 ? nlv : 1) * 8));
         const size_t small = 2 * (size_t)plen + (p + q + 1) + 16 + 3 * (size_t)p * nlv + (size_t)q * nlv + nlv +
                              2 * (p + q) + 64 + 16;
         JCB_TRY(ensure(c->hSmall, small * 8));
         s.dX = (double*)c->hX.p;
-        s.dY = (double*)c->hY.p;
+        s.dY = s.dX + (size_t)s.ld * p;
         s.dw = w ? (double*)c->hW.p : nullptr;
         s.dwout = (double*)c->hW.p + s.ld;
         s.dT = (double*)c->hT.p;
@@ -891,8 +890,12 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     const Ctx::Resident* rx = resident_find(c, X, ldx, n, p);
     const Ctx::Resident* ry = resident_find(c, Y, ldy, n, q);
     const int64_t ld = even_up(n);
-    if (!rx) JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
-    if (!ry) JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
+    // X and Y are staged in ONE buffer, Y's columns right behind X's: K1 then sees a single n x (p + q) matrix
+    // (launch_gram_to: joint column space)
+    const bool stage_xy = !rx && !ry;
+    if (stage_xy) JCB_TRY(ensure(c->hX, (size_t)ld * (p + q) * 8));
+    else if (!rx) JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
+    if (!ry && !stage_xy) JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
     if (!rx || !ry) invalidate_cv(c);
     JCB_TRY(ensure(c->hW, (size_t)ld * 2 * 8));
     JCB_TRY(ensure(c->hT, (size_t)ld * (nlv > 0 ? nlv : 1) * 8));
@@ -900,7 +903,7 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
                                  (size_t)q * nlv + nlv + 2 * (p + q) + 64;
     JCB_TRY(ensure(c->hSmall, small_doubles * 8));
     double* dX = rx ? rx->dev : (double*)c->hX.p;
-    double* dY = ry ? ry->dev : (double*)c->hY.p;
+    double* dY = ry ? ry->dev : (stage_xy ? (double*)c->hX.p + (size_t)ld * p : (double*)c->hY.p);
     const int64_t ldX = rx ? rx->ld : ld, ldY = ry ? ry->ld : ld;
     double* dw = w ? (double*)c->hW.p : nullptr;
     double* dwout = (double*)c->hW.p + ld;
@@ -1590,8 +1593,7 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
         JCB_TRY(ensure(c->hX, (size_t)ld * p * 8));
         JCB_TRY(ensure(c->hY, (size_t)ld * q * 8));
     }
-    JCB_TRY(ensure(c->cvX, (size_t)ldp * p * 8));
-    JCB_TRY(ensure(c->cvY, (size_t)ldp * q * 8));
+    JCB_TRY(ensure(c->cvX, (size_t)ldp * (p + q) * 8));          // permuted [X | Y] in one buffer (joint column space)
     JCB_TRY(ensure(c->cvIdx, (size_t)ldp * 8));
     JCB_TRY(ensure(c->hT, (size_t)even_up(maxlen) * ka * 8));
     JCB_TRY(ensure(c->hPred, (size_t)even_up(maxlen) * 2 * q * 8));
@@ -1603,7 +1605,7 @@ int jcb200_gridcv(const double* X, int64_t ldx, const double* Y, int64_t ldy, in
     double* dX = res ? rx->dev : (double*)c->hX.p;
     double* dY = res ? ry->dev : (double*)c->hY.p;
     double* dXp = (double*)c->cvX.p;
-    double* dYp = (double*)c->cvY.p;
+    double* dYp = dXp + (size_t)ldp * p;
     int64_t* dIdx = (int64_t*)c->cvIdx.p;
     double* dT = (double*)c->hT.p;
     double* dYaug = (double*)c->hPred.p;

@@ -483,7 +483,7 @@ gram_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
 __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restrict__ group_seg,
                    const double* __restrict__ partials, const ReduceDst dst, int p, int q,
-                   int nbx, int accumulate) {
+                   int nbx, int accumulate, int joint) {
     __shared__ double tile[32 * 33];
     const int gi = blockIdx.x / NCW, wu = blockIdx.x % NCW;
     const GroupDesc* gd = &groups[gi];
@@ -517,7 +517,10 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
             } else {
                 const int col = colbase + (e - 1024);
                 int64_t off = -1;
-                if (!by) {
+                if (joint) {                 // one column space [X | Y]: the block may straddle the two
+                    if (col < p) off = o_sx + col;
+                    else if (col < p + q) off = o_sy + (col - p);
+                } else if (!by) {
                     if (col < p) off = o_sx + col;
                 } else {
                     if (col < q) off = o_sy + col;
@@ -536,7 +539,14 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
             if (u.kind == 2 && (r >> 3) > (cl >> 3)) continue;      // below the diagonal: never computed
             const int row = rowbase + r, col = colbase + cl;
             int64_t off = -1;
-            if (!ay && !by) {
+            if (joint) {
+                if (col < p) {
+                    if (row < p) off = row + (int64_t)col * P;                               // X'X
+                } else if (col < p + q) {
+                    if (row < p) off = o_gxy + row + (int64_t)(col - p) * P;                 // X'Y
+                    else if (row == col) off = o_gyy + (row - p);                            // diag Y'Y
+                }
+            } else if (!ay && !by) {
                 if (row < p && col < p) off = row + (int64_t)col * P;
             } else if (!ay && by) {
                 if (row < p && col < q) off = o_gxy + row + (int64_t)col * P;
@@ -976,11 +986,23 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     }
     const int64_t nstages = (n + KT - 1) / KT;
     const int ncta = c->num_sms;
-    const int nbx = (int)((p + CB - 1) / CB);
-    // ---- schedule (cached on (p, q, nstages))
-    if (c->sk_p != p || c->sk_q != q || c->sk_nst != nstages) {
+    // Joint column space: when Y lies right behind X in memory with the same leading dimension (the library's own
+    // staging buffers; `device.colmajor_empty_xy`), [X | Y] IS one n x (p + q) matrix and the whole packed Gram is
+    // the upper triangle of ITS Gram: no separate Y blocks — Y's q columns ride in the padding of X's last
+    // 32-column block (p = 500: 20 + 10 of 32) instead of costing a 16-column-wide X'Y unit per X block (-5 % of the
+    // kernel's FP64-pipe time at C2).  K1b maps the joint coordinates back to the packed layout.
+    static int joint_ok = -1;
+    if (joint_ok < 0) {
+        const char* e = getenv("JCB_GRAM_JOINT");
+        joint_ok = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool joint = joint_ok && dY == dX + p * ldx && ldy == ldx;
+    const int64_t pj = joint ? p + q : p, qj = joint ? 0 : q;      // what the kernel sees
+    const int nbx = (int)((pj + CB - 1) / CB);
+    // ---- schedule (cached on (pj, qj, nstages))
+    if (c->sk_p != pj || c->sk_q != qj || c->sk_nst != nstages) {
         Schedule S;
-        build_groups(p, q, S);
+        build_groups(pj, qj, S);
         // zone = the row range all CTAs sweep together; sized so that one zone of [X Y] (~40 MB) stays
         // in the 126 MB L2 while the groups that share its column blocks read it.  With more groups
         // than CTAs there is nothing to co-schedule: one zone.
@@ -988,7 +1010,7 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
         const char* zenv = getenv("JCB_ZONE_MB");
         const double zone_mb = zenv ? atof(zenv) : 40.0;
         if ((int)S.groups.size() * 2 <= ncta && zone_mb > 0) {
-            const int64_t rows = (int64_t)(zone_mb * 1e6 / ((double)(p + q) * 8.0));
+            const int64_t rows = (int64_t)(zone_mb * 1e6 / ((double)(pj + qj) * 8.0));
             zone_len = std::max<int64_t>(16, rows / KT);
             if (zone_len > nstages) zone_len = nstages;
         }
@@ -1017,8 +1039,8 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
         c->sk_off_segs = gb;
         c->sk_off_cta = gb + sb;
         c->sk_off_gseg = gb + sb + cb;
-        c->sk_p = p;
-        c->sk_q = q;
+        c->sk_p = pj;
+        c->sk_q = qj;
         c->sk_nst = nstages;
         c->sk_ngroups = (int)S.groups.size();
         c->sk_nsegs = (int)S.segs.size();
@@ -1032,8 +1054,9 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     JCB_TRY(ensure(c->partials, (size_t)nsegs * NCW * UNIT_STRIDE * 8));
 
     CUtensorMap mapX, mapY, mapW;
-    JCB_TRY(make_map_2d(&mapX, dX, n, p, ldx, KT, 4 * CB));
-    JCB_TRY(make_map_2d(&mapY, dY, n, q, ldy, KT, 4 * CB));
+    JCB_TRY(make_map_2d(&mapX, dX, n, pj, ldx, KT, 4 * CB));
+    if (joint) mapY = mapX;
+    else JCB_TRY(make_map_2d(&mapY, dY, n, q, ldy, KT, 4 * CB));
     if (dw) {
         JCB_TRY(make_map_1d(&mapW, dw, n, KT));
     } else {
@@ -1049,8 +1072,8 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     prm.nst = nstages;
     prm.zone_len = (int32_t)c->sk_zone_len;
     prm.nzones = (int32_t)((nstages + c->sk_zone_len - 1) / c->sk_zone_len);
-    prm.p = (int)p;
-    prm.q = (int)q;
+    prm.p = (int)pj;
+    prm.q = (int)qj;
     prm.nbx = nbx;
     prm.weighted = dw ? 1 : 0;
 #ifdef JCB_K1_TRACE
@@ -1083,7 +1106,7 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     phase_end(c, JCB200_T_GRAM);
     phase_begin(c, JCB200_T_REDUCE);
     gram_reduce_kernel<<<ng * NCW, 256, 0, c->stream>>>(dgroups, dgseg, (const double*)c->partials.p,
-                                                        dst, (int)p, (int)q, nbx, accumulate);
+                                                        dst, (int)p, (int)q, nbx, accumulate, joint ? 1 : 0);
     JCB_LAUNCH_CHECK();
     phase_end(c, JCB200_T_REDUCE);
     return 0;

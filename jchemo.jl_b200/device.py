@@ -25,6 +25,13 @@ def colmajor_empty(n, p, device="cuda"):
     return torch.empty((p, even_up(n)), dtype=torch.float64, device=device)
 
 
+def colmajor_empty_xy(n, p, q, device="cuda"):
+    """X [p, ld] and Y [q, ld] as views of ONE [(p + q), ld] tensor: Y's columns lie right behind X's, so the Gram
+    kernel sees a single n x (p + q) matrix (joint column space: no separate X'Y blocks, csrc/k1_gram.cu)."""
+    t = torch.empty((p + q, even_up(n)), dtype=torch.float64, device=device)
+    return t[:p], t[p:]
+
+
 def use_current_stream():
     """Launch the library's kernels on torch's current stream (so torch.cuda.Event sees them)."""
     _lib.check(_lib.lib().jcb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1),
