@@ -748,14 +748,17 @@ struct Schedule {
     std::vector<int32_t> group_seg;  // ngroups + 1
 };
 
-// Fixed per-stage overhead of a group in the same units as unit_cost (fragment transforms, barrier).
-static double stage_overhead() {
-    static double v = -1;
-    if (v < 0) {
+// Fixed per-stage overhead of a group in the same units as unit_cost (fragment transforms, barrier).  Calibrated on
+// B200 with the joint [X | Y] layout (bench/k1_sweep.py, profiles/k1_sweep_r02.txt): when the groups are few and the
+// rows are swept in zones (C2: 10 groups, C3: 36) the optimum is 2-3 (C2 8.12 -> 8.06 ms), when there are about as
+// many groups as SMs (C4: 136) it is 5 (153.8 ms; 156.8 at 3, 158.5 at 2).  JCB_STAGE_OVERHEAD overrides both.
+static double stage_overhead(bool zoned) {
+    static double v = -2;
+    if (v < -1) {
         const char* e = getenv("JCB_STAGE_OVERHEAD");
-        v = e ? atof(e) : 5.0;   // calibrated on B200 at C2 (profiles/k1_r01_notes.md)
+        v = e ? atof(e) : -1.0;
     }
-    return v;
+    return v >= 0 ? v : (zoned ? 3.0 : 5.0);
 }
 
 static void build_groups(int64_t p, int64_t q, Schedule& S) {
@@ -817,7 +820,7 @@ static void build_groups(int64_t p, int64_t q, Schedule& S) {
             }
             double mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
             S.groups.push_back(gd);
-            S.gcost.push_back(mx + stage_overhead());
+            S.gcost.push_back(mx);              // + the per-stage overhead, added once the regime is known
         }
     };
     bool sw_assigned = false;
@@ -1003,13 +1006,15 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     if (c->sk_p != pj || c->sk_q != qj || c->sk_nst != nstages) {
         Schedule S;
         build_groups(pj, qj, S);
-        // zone = the row range all CTAs sweep together; sized so that one zone of [X Y] (~40 MB) stays
+        // zone = the row range all CTAs sweep together; sized so that one zone of [X Y] (~25 MB) stays
         // in the 126 MB L2 while the groups that share its column blocks read it.  With more groups
         // than CTAs there is nothing to co-schedule: one zone.
         int64_t zone_len = nstages;
         const char* zenv = getenv("JCB_ZONE_MB");
-        const double zone_mb = zenv ? atof(zenv) : 40.0;
-        if ((int)S.groups.size() * 2 <= ncta && zone_mb > 0) {
+        const double zone_mb = zenv ? atof(zenv) : 25.0;
+        const bool zoned = (int)S.groups.size() * 2 <= ncta && zone_mb > 0;
+        for (double& g : S.gcost) g += stage_overhead(zoned);
+        if (zoned) {
             const int64_t rows = (int64_t)(zone_mb * 1e6 / ((double)(pj + qj) * 8.0));
             zone_len = std::max<int64_t>(16, rows / KT);
             if (zone_len > nstages) zone_len = nstages;
