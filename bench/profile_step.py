@@ -17,7 +17,7 @@ ap.add_argument("--scal", action="store_true")
 a = ap.parse_args()
 torch.cuda.set_device(0)
 dev.init(0); dev.use_current_stream()
-X = dev.colmajor_empty(a.n, a.p); Y = dev.colmajor_empty(a.n, a.q)
+X, Y = dev.colmajor_empty_xy(a.n, a.p, a.q)      # the layout bench.py uses: Y right behind X
 dev.fill_uniform(X, a.n, 1); dev.fill_uniform(Y, a.n, 2)
 w = None
 if a.weighted:
