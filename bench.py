@@ -429,7 +429,7 @@ def main():
     achieved = f_gram(n_loc, P, Q) / (gram_avg * 1e-3) * 1e-12 if gram_avg else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic_r01.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic_r02.json")))["dram_bytes_per_launch"]
         traffic = traffic * n_loc / N_GLOBAL       # captured at 1e6 rows per launch
     except Exception:
         pass
