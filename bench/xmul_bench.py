@@ -15,6 +15,7 @@ ap.add_argument("--p", type=int, default=500)
 ap.add_argument("--q", type=int, default=10)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--tag", default="")
+ap.add_argument("--nlvs", default="25,50")
 a = ap.parse_args()
 torch.cuda.set_device(0); dev.init(0); dev.use_current_stream()
 root = os.path.join(os.path.dirname(__file__), "..")
@@ -43,7 +44,7 @@ def run(name, fn, by, fl):
                  "frac_of_bound": round(bound / ms, 3), "GBps": round(by / ms * 1e-6, 1), "tflops": round(fl / ms * 1e-9, 2)}
 
 
-for nlv in (25, 50):
+for nlv in [int(v) for v in a.nlvs.split(',')]:
     model = dev.DeviceModel(m, p, q, nlv)
     pivot = torch.empty(p + q + 1, dtype=torch.float64, device="cuda")
     sharded.fit_sharded(X, Y, None, m, model, pivot=pivot)

@@ -49,6 +49,7 @@ struct XmulParams {
     int64_t ldo;
     int ncol;              // real output columns in this pass
     int aligned;           // X is 16-byte aligned with even ldx: bulk copies allowed
+    int out_aligned;       // Out is 16-byte aligned with an even ldo: the direct epilogue may use 16-byte stores
     int direct;            // !SWEEP: results go from the accumulator fragments straight to global memory (no
                            // staging tile in shared memory: room for one more pipeline stage)
     const double* cflag;   // device flag of the fit (pivot[p+q]): != 1.0 = every column has mean^2 <= 64 var, so the
@@ -86,12 +87,13 @@ __global__ void xmul_pack_kernel(const double* __restrict__ M, int64_t ldm, cons
 
 // the sweep epilogue (51 prefix sums and 51 x q stores per row) runs on its own warps so that it overlaps the
 // consumers' DMMA work on the next tile instead of serialising with it.  Its DFMAs queue behind the DMMAs on
-// the shared FP64 pipe (each waits about one DMMA slot), so the work is spread over as many warps as there
-// are consumers: one row per thread, every second response per warp.
+// the shared FP64 pipe, so the work is spread over many warps: NCW - 1 of them (with the producer warp the CTA then
+// has 2 NCW warps = 512 threads at NCW = 8, i.e. 128 registers per thread for the consumers; one warp more and
+// ptxas caps everybody at 96), tasks of (32 rows, one response) dealt round-robin.
 template <bool SWEEP, int NCW>
-__host__ __device__ constexpr int xm_epw() { return SWEEP ? NCW : 0; }
+__host__ __device__ constexpr int xm_epw() { return SWEEP ? NCW - 1 : 0; }
 
-template <int NPB, int NEX, bool SWEEP, int NCW>
+template <int NPB, int NEX, bool SWEEP, int NCW, bool DIRECT>
 __global__ void __launch_bounds__((NCW + 1 + xm_epw<SWEEP, NCW>()) * 32, XM_OCC)
 xmul_kernel(const XmulParams prm) {
     constexpr int XM_NCW = NCW;
@@ -111,7 +113,9 @@ xmul_kernel(const XmulParams prm) {
     const int nstage = prm.nstage;
     unsigned char* stage_base = smem;
     double* out_s = reinterpret_cast<double*>(smem + (size_t)nstage * STAGE);   // [NPT][132]
-    const bool direct = !SWEEP && prm.direct != 0;
+    // DIRECT is a template parameter: the epilogue that is not used must not be in the kernel (register allocation
+    // and the placement of the leftover DFMAs in the main loop moved by 5 % with unrelated epilogue code present)
+    constexpr bool direct = !SWEEP && DIRECT;
     double* mu_s = out_s + (direct ? 0 : NPT * XM_PITCH);                         // nchunk*32
     double* cy_s = mu_s + prm.nchunk * XM_KC;                                    // ncol*q (sweep only)
     double* cb_s = cy_s + (SWEEP ? ((prm.ncol * prm.q + 1) & ~1) : 0);          // NPT (+ pad): -mu'M, centre-free path
@@ -200,40 +204,47 @@ xmul_kernel(const XmulParams prm) {
 
     if (SWEEP && warp > XM_NCW) {
         // ------------------------------------------------------------------ sweep epilogue warps
-        // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j]: one row per thread, k outer, up to 8
-        // responses carried in registers (independent chains), Cy from shared memory; a warp's store
-        // covers 32 consecutive rows of one column (256 bytes)
+        // pred_k[row, j] = ymeans[j] + sum_{l<k} T[row, l] * Cy[l][j].  A task = (group of 32 rows, response j):
+        // one row per lane, k outer, up to 6 tasks of a warp carried in registers (independent DFMA chains), Cy
+        // from shared memory; a warp's store covers 32 consecutive rows of one column (256 bytes)
         const int ew = warp - XM_NCW - 1;
-        const int r = (ew % (XM_MT / 32)) * 32 + lane;
-        const int jh = ew / (XM_MT / 32);                 // 0 / 1: even / odd responses
+        constexpr int NRG = XM_MT / 32, NT = 6;
         const int q = prm.q;
+        const int ntask = NRG * q;
         const int64_t msz = prm.m * (int64_t)q;
         uint32_t tn = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tn) {
             const int64_t row0 = t * XM_MT;
-            const bool rok = row0 + r < prm.m;
             mbar_wait(tfull, tn & 1);
-            for (int j0 = jh; j0 < q; j0 += 16) {
-                double pv[8];
+            for (int base = ew; base < ntask; base += XM_EPW * NT) {
+                double pv[NT];
+                const double* ts[NT];
+                const double* cy[NT];
+                double* dk[NT];
+                bool ok[NT];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) pv[u] = (j0 + 2 * u < q) ? prm.ymeans[j0 + 2 * u] : 0.0;
-                double* dk = prm.Pred + row0 + r + (int64_t)j0 * prm.m;
-                const double* ts = out_s + r;
-                const double* cy = cy_s + j0;
+                for (int u = 0; u < NT; ++u) {
+                    const int task = base + u * XM_EPW;
+                    const bool valid = task < ntask;
+                    const int rg = valid ? task / q : 0, j = valid ? task - rg * q : 0;
+                    const int r = rg * 32 + lane;
+                    pv[u] = prm.ymeans[j];
+                    ts[u] = out_s + r;
+                    cy[u] = cy_s + j;
+                    dk[u] = prm.Pred + row0 + r + (int64_t)j * prm.m;
+                    ok[u] = valid && row0 + r < prm.m;
+                }
                 for (int k = 0; k <= prm.k_hi; ++k) {
                     if (k >= prm.k_lo) {
-                        if (rok) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (j0 + 2 * u < q) __stcs(dk + (int64_t)(2 * u) * prm.m, pv[u]);
+                        for (int u = 0; u < NT; ++u) {
+                            if (ok[u]) __stcs(dk[u], pv[u]);
+                            dk[u] += msz;
                         }
-                        dk += msz;
                     }
                     if (k < prm.k_hi) {
-                        const double tv = ts[k * XM_PITCH];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (j0 + 2 * u < q) pv[u] = fma(tv, cy[k * q + 2 * u], pv[u]);
+                        for (int u = 0; u < NT; ++u) pv[u] = fma(ts[u][k * XM_PITCH], cy[u][k * q], pv[u]);
                     }
                 }
             }
@@ -296,37 +307,54 @@ xmul_kernel(const XmulParams prm) {
         };
         if (center) chunk_loop(std::true_type{});
         else chunk_loop(std::false_type{});
-        if (direct) {
-            // ---- epilogue, direct: lane (g, kk) holds rows m0 + 2g + h, columns nb*8 + 2kk (+1): for one
-            // register the eight g-lanes of a column write eight rows two apart, the h = 0 / 1 stores fill
-            // each other's gaps (merged in L2; the result is 5 % of the kernel's traffic)
+        if constexpr (direct) {
+            // ---- epilogue, direct: lane (g, kk) holds rows m0 + 2g, m0 + 2g + 1 (h = 0, 1) of columns
+            // nb*8 + 2kk (+1).  The two rows of a column go out as ONE 16-byte store, so a warp-wide store covers
+            // four columns x 128 contiguous bytes (16 full sectors instead of 32 half-written ones: -5 % at
+            // nlv = 16, neutral at 24+).  Unaligned outputs and the ragged last rows fall back to 8-byte stores.
+            // What the result stores cost (round 2, JCB_XM_DBG_L2 builds, profiles/r02_xmul_decomposition.md):
+            // 2.7 us of a 30 us tile at nlv = 24 although they are 5 % of the bytes — they queue in the LSU in front
+            // of the next tile's fragment loads.  Sending them through the TMA engine instead (results written over
+            // the warp's own rows of the tile's last stage, one 128-byte bulk copy per column) was built and
+            // measured: -3.5 % at nlv = 24, +5 % at nlv = 25, +2 % at 16 — the bulk stores queue behind the
+            // producer's loads and hold the stage back; not kept.
+            const int row = m0 + 2 * g;
+            double* o = prm.Out + row0 + row;
+            const bool vec = prm.out_aligned && row + 1 < rows;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int row = m0 + 2 * g + h;
-                double* o = prm.Out + row0 + row;
+            for (int nb = 0; nb < NPB; ++nb) {
 #pragma unroll
-                for (int nb = 0; nb < NPB; ++nb) {
-#pragma unroll
-                    for (int e2 = 0; e2 < 2; ++e2) {
-                        const int col = nb * 8 + 2 * kk + e2;
-                        if (row < rows && col < prm.ncol) {
-                            double v = acc[h][nb][e2];
-                            if (!center) v += cb_s[col];
-                            if (prm.bias) v += prm.bias[col];
-                            o[(int64_t)col * prm.ldo] = v;
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int col = nb * 8 + 2 * kk + e2;
+                    if (col < prm.ncol) {
+                        double v0 = acc[0][nb][e2], v1 = acc[1][nb][e2];
+                        double add = 0.0;
+                        if (!center) add += cb_s[col];
+                        if (prm.bias) add += prm.bias[col];
+                        v0 += add;
+                        v1 += add;
+                        double* oc = o + (int64_t)col * prm.ldo;
+                        if (vec) {
+                            *reinterpret_cast<double2*>(oc) = make_double2(v0, v1);
+                        } else {
+                            if (row < rows) oc[0] = v0;
+                            if (row + 1 < rows) oc[1] = v1;
                         }
                     }
                 }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int e = 0; e < NEX; ++e) {
                     double v = ex[h][e];                  // partial over this lane's k (kk); sum the 4 kk lanes
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     const int col = NP + e;
-                    if (kk == 0 && row < rows && col < prm.ncol) {
+                    if (kk == 0 && row + h < rows && col < prm.ncol) {
                         if (!center) v += cb_s[col];
                         if (prm.bias) v += prm.bias[col];
-                        o[(int64_t)col * prm.ldo] = v;
+                        o[h + (int64_t)col * prm.ldo] = v;
                     }
                 }
             }
@@ -413,11 +441,19 @@ static int launch_xmul_w(Ctx* c, XmulParams& prm) {
     }
     prm.nstage = nstage;
     const int smem = nstage * stage + fixed;
-    JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
     const int64_t ntiles = (prm.m + XM_MT - 1) / XM_MT;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)XM_OCC * c->num_sms);
-    xmul_kernel<NPB, NEX, SWEEP, NCW><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+    if (!SWEEP && prm.direct) {
+        if constexpr (!SWEEP) {
+            JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            xmul_kernel<NPB, NEX, SWEEP, NCW, true><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+        }
+    } else {
+        JCB_CUDA(cudaFuncSetAttribute(xmul_kernel<NPB, NEX, SWEEP, NCW, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        xmul_kernel<NPB, NEX, SWEEP, NCW, false><<<grid, XM_THREADS, smem, c->stream>>>(prm);
+    }
     JCB_LAUNCH_CHECK();
     return 0;
 }
@@ -515,6 +551,7 @@ static int xmul_common(Ctx* c, const double* dX, int64_t ldx, int64_t m, int64_t
         prm.ldo = ldo;
         prm.ncol = ncol;
         prm.aligned = aligned;
+        prm.out_aligned = (prm.Out && (((uintptr_t)prm.Out & 15) == 0) && (ldo & 1) == 0) ? 1 : 0;
         prm.cflag = sweep ? nullptr : c->xmul_center_flag;
         if (sweep) {
             sweep_cy_kernel<<<(ncol * q + 255) / 256, 256, 0, c->stream>>>(dC, dys, q, ncol, Cy);
