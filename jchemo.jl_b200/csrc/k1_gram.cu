@@ -41,6 +41,10 @@ namespace jcb {
 #ifndef JCB_NSTAGE
 #define JCB_NSTAGE 2
 #endif
+#ifndef JCB_POLL_MOD
+#define JCB_POLL_MOD 4
+#define JCB_POLL_REM 1
+#endif
 constexpr int KT = JCB_KT;             // rows per pipeline stage (KT % 16 == 8: conflict-free LDS.128)
 constexpr int CB = 32;                 // columns per block
 constexpr int MAXSLOT = 8;             // column blocks staged per stage
@@ -146,7 +150,12 @@ __device__ __forceinline__ void stage_steps(const double* __restrict__ tA, const
         // them within one step of each other.
         if (bar_threads > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
 #endif
-        poll();
+        // thread 0 looks for a released ring slot at k8-steps 1 and 5 of the 7.  The poll sits on warp 0's critical
+        // path: every k8-step 0.871 of the FP64 peak at C2, every second 0.878, steps 1 and 5 0.879 (C3 0.878 ->
+        // 0.889, C4 shard 0.886 -> 0.897), once per stage 0.845-0.863, never (blocking only) 0.79; twice per k8-step,
+        // or issuing from the warp that completes the release, makes the 16 warps run in lockstep and lose more at
+        // the stage boundaries than the earlier refill gains (0.835).
+        if ((k8 % JCB_POLL_MOD) == JCB_POLL_REM) poll();
         double2 a[MBC];
 #pragma unroll
         for (int mb = 0; mb < MBC; ++mb)
