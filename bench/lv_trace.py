@@ -14,7 +14,7 @@ torch.cuda.synchronize()
 raw = C.CDLL(os.environ["JCB_LIB"])
 buf = (C.c_longlong * 24)()
 raw.jcb200_debug_lv_trace(buf)
-names = ["A: M partial, exchange, sum", "eigenvector", "-", "B: sum of partials + sync (after wait)", "C: r, gather, u, wait", "D: matvec + send", "D: wait", "tt, c", "-", "deflate + store",
+names = ["A: M partial, exchange, sum", "eigenvector: wait for the Z warps (ZF)", "eigenvector + v'Mv (warp 0)", "B: sum of partials + sync (after wait)", "C: r, gather, u, wait", "D: matvec + send", "D: wait", "tt, c", "-", "deflate + store",
          "B: w~ + sync", "B: dots + send", "B: wait"]
 if os.environ.get("JCB_LV_LINEAR", "1") != "0":
     n0 = ["t0: partial M,Z + send", "t0: wait A", "t0: sum A + sync", "t0: eigenvector", "t0: wait D (builders' branch)",

@@ -591,8 +591,9 @@ static_assert(LV_THREADS / 32 == LV16_CLUSTER, "warp w sends to CTA w: one warp 
 
 struct LvdLayout {
     int pe, sp, xs, Ps, Rs, w, r, zp, rfull, exA, exB, exU, exD, M, A, B, v, c, d, red, g, total;   // doubles
+    int lenZ, zloc, exZ, Zs;     // ZF: this CTA's partial Z = P_c'XtY_c, the 16 slots it is exchanged through, the sum
 };
-__host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, bool gs) {
+__host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, bool gs, bool zf = false) {
     LvdLayout L;
     auto ev = [](int x) { return (x + 1) & ~1; };
     const int nt = q * (q + 1) / 2;
@@ -617,6 +618,10 @@ __host__ __device__ inline LvdLayout lvd_layout(int p, int q, int nlv, int per, 
     L.c = o; o += ev(q);
     L.d = o; o += ev(nlv + 1);
     L.red = o; o += 32;
+    L.lenZ = ev(nlv * q);
+    L.zloc = o; o += zf ? L.lenZ : 0;
+    L.exZ = o; o += zf ? LV16_CLUSTER * L.lenZ : 0;
+    L.Zs = o; o += zf ? L.lenZ : 0;
     L.g = o; o += gs ? per * L.pe : 0;
     L.total = o;
     return L;
@@ -648,19 +653,28 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
                  : "memory");
 }
 
-template <bool GS>
+// ZF (q > 1): the Gram-Schmidt dots d = P'w~ and |w~|^2 need no exchange of their own.  w~ = XtY v, so d = (P'XtY) v
+// = Z v and |w~|^2 = v'M v: every CTA sends its partial Z_c = P_c'XtY_c (a x q doubles, one bulk DSMEM copy per
+// peer) right beside its partial M, the copies and the ordered sum over the 16 slots run on warps 1-15 WHILE warp 0
+// iterates the eigenvector, and exchange B (dots, send, wait, sum: 3.3 K of an LV's 20 K cycles) disappears.
+template <bool GS, bool ZF>
 __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams prm) {
     if (prm.status[0] != 0.0) return;          // non-finite input: every CTA leaves before the first barrier
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double sm[];
-    __shared__ __align__(8) uint64_t bars[5];          // A, B, C, D, B2 (the rare w = e_1 redo)
+    __shared__ __align__(8) uint64_t bars[6];          // A, B, C, D, B2 (the rare w = e_1 redo), Z
     const int p = prm.p, q = prm.q, nlv = prm.nlv;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = LV_THREADS >> 5;
     const int rank = (int)cluster.block_rank();
     constexpr int ncta = LV16_CLUSTER;
     const int per = (p + ncta - 1) / ncta;
     const int lo = min(p, rank * per), hi = min(p, lo + per), nsl = hi - lo;
-    const LvdLayout L = lvd_layout(p, q, nlv, per, GS);
+    const LvdLayout L = lvd_layout(p, q, nlv, per, GS, ZF);
+    const bool zf = ZF && q > 1;
+    const int lenZ = L.lenZ;
+    double* zloc = sm + L.zloc;
+    double* exZ = sm + L.exZ;
+    double* Zs = sm + L.Zs;
     const int pe = L.pe, sp = L.sp, nt = q * (q + 1) / 2, nd = nlv + 1;
     double* rfull = sm + L.rfull;
     double* xs = sm + L.xs;
@@ -683,16 +697,18 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
     double* g_s = sm + L.g;
     const int64_t P64 = p;
     const uint32_t barA = smem_u32(&bars[0]), barB = smem_u32(&bars[1]), barC = smem_u32(&bars[2]),
-                   barD = smem_u32(&bars[3]), barB2 = smem_u32(&bars[4]);
+                   barD = smem_u32(&bars[3]), barB2 = smem_u32(&bars[4]), barZ = smem_u32(&bars[5]);
+    auto evn = [](int x) { return (x + 1) & ~1; };
     const uint32_t bytesA = (uint32_t)(ncta * nt * 8), bytesC = (uint32_t)((p + ncta * q) * 8),
                    bytesD = (uint32_t)(ncta * 8);
 
     if (tid == 0) {
-        for (int b = 0; b < 5; ++b) mbar_init(&bars[b], 1);
+        for (int b = 0; b < 6; ++b) mbar_init(&bars[b], 1);
         fence_barrier_init();
         // arm LV 0 (a peer's data may arrive before the arming of a phase: the pending arrival keeps it open)
         if (q > 1) mbar_arrive_expect_tx(&bars[0], bytesA);
-        mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * 8));
+        if (!zf) mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * 8));
+        if (zf && nlv > 1) mbar_arrive_expect_tx(&bars[5], (uint32_t)(ncta * evn(q) * 8));   // Z of LV 1
         mbar_arrive_expect_tx(&bars[2], bytesC);
         mbar_arrive_expect_tx(&bars[3], bytesD);
     }
@@ -763,6 +779,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
         LV_MARK(9);
         // ---------------------------------------------------------------- A: M = XtY'XtY, v
         if (q > 1) {
+            double mval = 0.0;
             if (tid < nt) {
                 const double* ci = xs + ti * sp;
                 const double* cj = xs + tj * sp;
@@ -775,11 +792,13 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
                     s3 += ci[k + 3] * cj[k + 3];
                 }
                 for (; k < nsl; ++k) s0 += ci[k] * cj[k];
-                const double val = (s0 + s1) + (s2 + s3);
+                mval = (s0 + s1) + (s2 + s3);
                 // one destination CTA per st.async instruction (the lanes carry the entries of the triangle)
                 const uint32_t dst = smem_u32(exA + rank * nt + tid);
 #pragma unroll
-                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), val, mapa_u32(barA, cta));
+                for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), mval, mapa_u32(barA, cta));
+            }
+            if (tid < nt) {
                 mbar_wait(&bars[0], par);
                 if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], bytesA);
                 double v[ncta];
@@ -793,7 +812,68 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
             }
             __syncthreads();
             LV_MARK(0);
-            if (warp == 0) eig_dominant_warp_q(q, M_s, A_s, B_s, v_s, lane);
+            if (warp == 0) {
+                eig_dominant_warp_q(q, M_s, A_s, B_s, v_s, lane);
+                if (zf) {
+                    // |w~|^2 = v'M v
+                    double sv = 0.0;
+                    if (lane < q) {
+                        double t0 = 0.0, t1 = 0.0;
+                        int k = 0;
+                        for (; k + 1 < q; k += 2) {
+                            t0 += M_s[lane * q + k] * v_s[k];
+                            t1 += M_s[lane * q + k + 1] * v_s[k + 1];
+                        }
+                        if (k < q) t0 += M_s[lane * q + k] * v_s[k];
+                        sv = v_s[lane] * (t0 + t1);
+                    }
+                    sv = warp_sum(sv);
+                    if (lane == 0) d_s[a] = sv;
+                }
+                LV_MARK(2);
+            } else if (zf && a > 0 && (warp & 3) != 0) {
+                // beside the eigenvector iteration, on the 12 warps of the three OTHER SMSPs (warp 0's own SMSP is
+                // left to it): partial Z_c[j][k] = P_c[:, j]' XtY_c[:, k] for the a finished LVs, staged in zloc, sent
+                // to slot [rank] of every CTA's exZ by 16 bulk copies; one warp waits for the 16 incoming slots (15
+                // warps polling the barrier slowed the eigenvector warp down), then all 12 sum them in rank order
+                constexpr int NWORK = (LV_THREADS / 32 - LV_THREADS / 128) * 32;      // 384
+                const int wl = (warp - 1 - (warp >> 2)) * 32 + lane;
+                const int nz = a * q;
+                for (int e = wl; e < evn(nz); e += NWORK) {
+                    double s0 = 0.0, s1 = 0.0;
+                    if (e < nz) {
+                        const int j = e / q, k = e - j * q;
+                        const double* pc = Ps + j * sp;
+                        const double* xc = xs + k * sp;
+                        int i = 0;
+                        for (; i + 1 < nsl; i += 2) {
+                            s0 += pc[i] * xc[i];
+                            s1 += pc[i + 1] * xc[i + 1];
+                        }
+                        if (i < nsl) s0 += pc[i] * xc[i];
+                    }
+                    zloc[e] = s0 + s1;
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
+                if (wl < ncta)
+                    bulk_s2c(mapa_u32(smem_u32(exZ + rank * lenZ), wl), smem_u32(zloc), (uint32_t)(evn(nz) * 8),
+                             mapa_u32(barZ, wl));
+                if (warp == 1) {
+                    mbar_wait(&bars[5], (uint32_t)((a - 1) & 1));
+                    if (lane == 0 && more) mbar_arrive_expect_tx(&bars[5], (uint32_t)(ncta * evn(nz + q) * 8));
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
+                for (int e = wl; e < nz; e += NWORK) {
+                    double v[ncta];
+#pragma unroll
+                    for (int cta = 0; cta < ncta; ++cta) v[cta] = exZ[cta * lenZ + e];
+                    double s = 0.0;
+#pragma unroll
+                    for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+                    Zs[e] = s;
+                }
+            }
             __syncthreads();
             LV_MARK(1);
         }
@@ -806,23 +886,42 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
             }
             w_s[tid] = t;
         }
-        __syncthreads();
-        LV_MARK(10);
-        dots_and_send(a, barB);
-        LV_MARK(11);
-        if (tid <= a) {
-            mbar_wait(&bars[1], par);
+        if (zf) {
+            // d_j = Z[j, :] v (j < a) on warps 1.. (|w~|^2 = v'M v came with the eigenvector): no exchange
+            if (tid >= 32 && tid - 32 < a) {
+                const double* zr = Zs + (tid - 32) * q;
+                double s0 = 0.0, s1 = 0.0;
+                int k = 0;
+                for (; k + 1 < q; k += 2) {
+                    s0 += zr[k] * v_s[k];
+                    s1 += zr[k + 1] * v_s[k + 1];
+                }
+                if (k < q) s0 += zr[k] * v_s[k];
+                d_s[tid - 32] = s0 + s1;
+            }
+            __syncthreads();
+            LV_MARK(10);
+            LV_MARK(11);
             LV_MARK(12);
-            if (tid == 0 && more) mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * (a + 2) * 8));
-            double v[ncta];
+        } else {
+            __syncthreads();
+            LV_MARK(10);
+            dots_and_send(a, barB);
+            LV_MARK(11);
+            if (tid <= a) {
+                mbar_wait(&bars[1], par);
+                LV_MARK(12);
+                if (tid == 0 && more) mbar_arrive_expect_tx(&bars[1], (uint32_t)(ncta * (a + 2) * 8));
+                double v[ncta];
 #pragma unroll
-            for (int cta = 0; cta < ncta; ++cta) v[cta] = exB[cta * nd + tid];
-            double s = 0.0;
+                for (int cta = 0; cta < ncta; ++cta) v[cta] = exB[cta * nd + tid];
+                double s = 0.0;
 #pragma unroll
-            for (int cta = 0; cta < ncta; ++cta) s += v[cta];
-            d_s[tid] = s;
+                for (int cta = 0; cta < ncta; ++cta) s += v[cta];
+                d_s[tid] = s;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (!(d_s[a] > 0.0)) {
             // XtY == 0 (e.g. constant Y): LAPACK's svd of a zero matrix returns U = I, so the reference
             // takes w = e_1 (plskern.jl:154) and carries on with c = 0.  Redo the dots on e_1 (all CTAs
@@ -1515,9 +1614,16 @@ int launch_solve_src(Ctx* c, const PackedSrc& src, const double* d_pivot, int64_
         const size_t sm_gs = (size_t)lvd_layout((int)p, (int)q, nlv, per, true).total * 8;
         const size_t sm_l2 = (size_t)lvd_layout((int)p, (int)q, nlv, per, false).total * 8;
         const bool gs = sm_gs <= max_smem && getenv("JCB_LV_NO_GS") == nullptr;
-        const size_t smem16 = gs ? sm_gs : sm_l2;
+        // Z folded into exchange A (q > 1) when its 18 buffers of nlv * q doubles fit beside everything else
+        // (measured, round 2: C2 0.271 -> 0.252 ms; slices of 63 rows -2 %; C4, slices of 125 rows, +8 %: the partial Z
+        // costs a * q dot products over the slice per LV, beside a latency-bound eigenvector warp)
+        static const int zf_per_max = getenv("JCB_LV_ZF_PER") ? atoi(getenv("JCB_LV_ZF_PER")) : 64;
+        const bool zf = q > 1 && nlv <= LV_THREADS - 32 && per <= zf_per_max && getenv("JCB_LV_NO_ZF") == nullptr &&
+                        (size_t)lvd_layout((int)p, (int)q, nlv, per, gs, true).total * 8 <= max_smem;
+        const size_t smem16 = zf ? (size_t)lvd_layout((int)p, (int)q, nlv, per, gs, true).total * 8 : (gs ? sm_gs : sm_l2);
         if (smem16 <= max_smem) {
-            auto kern = gs ? lvdist_kernel<true> : lvdist_kernel<false>;
+            auto kern = gs ? (zf ? lvdist_kernel<true, true> : lvdist_kernel<true, false>)
+                           : (zf ? lvdist_kernel<false, true> : lvdist_kernel<false, false>);
             JCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
             JCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             cudaLaunchConfig_t cfg = {};
