@@ -263,7 +263,9 @@ static int host_sample_pivot(Ctx* c, const double* X, int64_t ldx, const double*
     JCB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cs));
     JCB_CUDA(cudaEventRecord(c->chunk_ev[2], cs));
     JCB_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ev[2], 0));
+    phase_begin(c, JCB200_T_PIVOT);          // after the wait: the phase is the kernel, not the copy it waits for
     JCB_TRY(launch_pivot(c, d, ns, d + ns * p, ns, ns, p, q, d_pivot));
+    phase_end(c, JCB200_T_PIVOT);
     return 0;
 }
 
@@ -958,12 +960,6 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
     JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));      // copies must not overtake earlier work on `st`
     JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
     phase_begin_on(c, JCB200_T_H2D, cs);
-    // the pivot of a streamed fit comes from a strided sample over all rows, sent ahead of the first chunk
-    if (chunked) {
-        phase_begin(c, JCB200_T_PIVOT);
-        JCB_TRY(host_sample_pivot(c, X, ldx, Y, ldy, n, p, q, d_pivot, cs));
-        phase_end(c, JCB200_T_PIVOT);
-    }
     if (w) JCB_TRY(h2d_2d(c, dw, ld, w, n, n, 1, cs));
     // Host-paced, one copy ahead: K1 on chunk i is enqueued when its rows have landed, right after the copy of
     // chunk i+1 has been issued.  With every copy queued up front a kernel enqueued behind them may not start
@@ -978,6 +974,10 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
         return 0;
     };
     JCB_TRY(issue_chunk(0));
+    // the pivot of a streamed fit comes from a strided sample over all rows.  The host gathers it (8 K short memcpys,
+    // ~0.4 ms at C2) WHILE the first chunk is on the link and queues it right behind that chunk: K1 on chunk 0 cannot
+    // start before the chunk has landed anyway (round 1-2 gathered first and left the link idle meanwhile).
+    if (chunked) JCB_TRY(host_sample_pivot(c, X, ldx, Y, ldy, n, p, q, d_pivot, cs));
     for (int ci = 0; ci < nchunks; ++ci) {
         const int64_t r0 = bounds[ci], nr = bounds[ci + 1] - r0;
         if (nchunks > 1) JCB_CUDA(cudaEventSynchronize(c->chunk_ev[1 + (ci & 1)]));
