@@ -78,6 +78,9 @@ int jcb200_set_stream(void* cuda_stream, int32_t external);
 int jcb200_last_timings(double* ms, int cap);
 /* Synchronise the library stream and collect the phase times of the preceding "_dev" calls. */
 int jcb200_sync_timings(void);
+/* Phase events on (default) / off.  Each record is a stream operation of its own; callers that time whole fits
+   themselves switch them off.  The K1 event ring (jcb200_gram_timings) stays on. */
+int jcb200_set_phase_timing(int on);
 /* Durations (ms, most recent first) of the last K1 Gram-kernel launches, from CUDA events recorded
  * around each launch on the launching stream; synchronises that stream.  Returns the count written
  * (negative/positive status codes on failure are not used here: at most `cap`, at most 256). */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "jcb200_set_stream": (C.c_int, [C.c_void_p, i32]),
     "jcb200_last_timings": (C.c_int, [c_dp, C.c_int]),
     "jcb200_sync_timings": (C.c_int, []),
+    "jcb200_set_phase_timing": (C.c_int, [C.c_int]),
     "jcb200_gram_timings": (C.c_int, [c_dp, C.c_int]),
     "jcb200_launch_count": (i64, []),
     "jcb200_host_register": (C.c_int, [C.c_void_p, i64]),

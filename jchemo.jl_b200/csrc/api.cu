@@ -54,7 +54,10 @@ int ensure(Buf& b, size_t bytes) {
 // Phase timers.  phase_begin/phase_end bracket ONE occurrence on the compute stream; a phase that occurs
 // several times in a call (K1 on every row chunk, K5 on every score block) is reported as the SUM of its
 // occurrences.  The *_on forms mark a SPAN on another stream (first begin .. last end): the copy legs.
+// phase events can be switched off (jcb200_set_phase_timing): every record is an operation of its own in the stream
+static bool g_phase_timing = true;
 void phase_begin(Ctx* c, int ph) {
+    if (!g_phase_timing) return;
     if (c->ev_open[ph]) return;
     if (c->ev_cnt[ph] >= Ctx::PHASE_SLOTS) c->ev_cnt[ph] = Ctx::PHASE_SLOTS - 1;   // out of slots: widen the last
     else cudaEventRecord(c->ev_begin[ph][c->ev_cnt[ph]], c->stream);
@@ -67,6 +70,7 @@ void phase_end(Ctx* c, int ph) {
     c->ev_open[ph] = false;
 }
 void phase_begin_on(Ctx* c, int ph, cudaStream_t st) {
+    if (!g_phase_timing) return;
     if (c->ev_cnt[ph] == 0 && !c->ev_open[ph]) {
         cudaEventRecord(c->ev_begin[ph][0], st);
         c->ev_open[ph] = true;
@@ -1738,6 +1742,15 @@ int jcb200_locw_plskern(const double* Xtrain, int64_t ldxt, const double* Ytrain
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
     phases_collect(c);
+    return 0;
+}
+
+/* phase events on / off (default on).  Every event record is an operation of its own in the stream; a caller that
+   times whole fits itself (bench.py's timed region) switches them off.  The per-launch event ring around K1
+   (jcb200_gram_timings) is not affected. */
+int jcb200_set_phase_timing(int on) {
+    API_PROLOGUE();
+    g_phase_timing = on != 0;
     return 0;
 }
 

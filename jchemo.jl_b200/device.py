@@ -183,6 +183,12 @@ def center_scale_dev(X, n, mu, sigma):
                "center_scale_dev")
 
 
+def set_phase_timing(on):
+    """Phase events on / off (the K1 event ring of gram_timings stays on): a caller that times whole fits itself
+    takes the per-phase event records out of its timed region."""
+    _lib.check(_lib.lib().jcb200_set_phase_timing(1 if on else 0), "set_phase_timing")
+
+
 def sync_timings():
     _lib.check(_lib.lib().jcb200_sync_timings(), "sync_timings")
     return _lib.last_timings()
