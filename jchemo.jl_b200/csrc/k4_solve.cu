@@ -779,7 +779,6 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
         LV_MARK(9);
         // ---------------------------------------------------------------- A: M = XtY'XtY, v
         if (q > 1) {
-            double mval = 0.0;
             if (tid < nt) {
                 const double* ci = xs + ti * sp;
                 const double* cj = xs + tj * sp;
@@ -792,13 +791,11 @@ __global__ void __launch_bounds__(LV_THREADS, 1) lvdist_kernel(const LvParams pr
                     s3 += ci[k + 3] * cj[k + 3];
                 }
                 for (; k < nsl; ++k) s0 += ci[k] * cj[k];
-                mval = (s0 + s1) + (s2 + s3);
+                const double mval = (s0 + s1) + (s2 + s3);
                 // one destination CTA per st.async instruction (the lanes carry the entries of the triangle)
                 const uint32_t dst = smem_u32(exA + rank * nt + tid);
 #pragma unroll
                 for (int cta = 0; cta < ncta; ++cta) st_async_f64(mapa_u32(dst, cta), mval, mapa_u32(barA, cta));
-            }
-            if (tid < nt) {
                 mbar_wait(&bars[0], par);
                 if (tid == 0 && more) mbar_arrive_expect_tx(&bars[0], bytesA);
                 double v[ncta];
