@@ -100,6 +100,21 @@ static void phases_collect(Ctx* c) {
                 cudaGetLastError();
         }
     }
+    // JCB_DEBUG_TIMELINE=1: where every occurrence of every phase sits inside the call (ms after the begin of TOTAL)
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("JCB_DEBUG_TIMELINE") ? 1 : 0;
+    if (dbg && c->ev_cnt[JCB200_T_TOTAL] > 0) {
+        for (int i = 0; i < JCB200_NPHASE; ++i)
+            for (int k = 0; k < c->ev_cnt[i]; ++k) {
+                float b = 0.f, e = 0.f;
+                if (cudaEventElapsedTime(&b, c->ev_begin[JCB200_T_TOTAL][0], c->ev_begin[i][k]) != cudaSuccess ||
+                    cudaEventElapsedTime(&e, c->ev_begin[JCB200_T_TOTAL][0], c->ev_end[i][k]) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                fprintf(stderr, "[jcb200 timeline] phase %d #%d  %9.3f .. %9.3f ms\n", i, k, b, e);
+            }
+    }
 }
 
 static Ctx g_extra[7];        // devices 1..ndev-1 of a single-process multi-GPU set (jcb200_init_multi)
@@ -1030,19 +1045,10 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
         JCB_CUDA(cudaEventRecord(c->blk_ev[nb_used], st));
     }
     JCB_TRY(launch_weights(c, dw, n, d_sumw, dwout));
-    if (nlv > 0) {
-        JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
-        JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
-        JCB_CUDA(cudaMemcpyAsync(W, dW, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
-        JCB_CUDA(cudaMemcpyAsync(C, dC, (size_t)q * nlv * 8, cudaMemcpyDeviceToHost, st));
-        JCB_CUDA(cudaMemcpyAsync(TT, dTT, (size_t)nlv * 8, cudaMemcpyDeviceToHost, st));
-    }
-    JCB_CUDA(cudaMemcpyAsync(xmeans, dxm, p * 8, cudaMemcpyDeviceToHost, st));
-    JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
-    JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
-    JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
-    if (!writeback_xy) JCB_CUDA(cudaMemcpyAsync(&status, d_sumw + 1, 8, cudaMemcpyDeviceToHost, st));
-    JCB_TRY(d2h_2d(c, w_out, n, dwout, ld, n, 1, st));
+    // The T (and X, Y) block copies go into the device-to-host queue FIRST: that queue is served in issue order across
+    // streams, and the small copies below wait (in their stream) for the last score block — queued ahead, they held
+    // the first T block back until every block had been scored (timeline, JCB_DEBUG_TIMELINE=1: the D2H leg began
+    // 0.88 ms late at C2).
     {
         int bi = 0;
         for (int64_t r0 = 0; r0 < n; r0 += blk, ++bi) {
@@ -1056,8 +1062,21 @@ int jcb200_plskern_fit(double* X, int64_t ldx, double* Y, int64_t ldy, const dou
             }
         }
         JCB_CUDA(cudaEventRecord(c->chunk_ev[0], cs));
-        JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));     // the block copies on the copy stream
     }
+    if (nlv > 0) {
+        JCB_CUDA(cudaMemcpyAsync(P, dP, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(R, dR, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(W, dW, (size_t)p * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(C, dC, (size_t)q * nlv * 8, cudaMemcpyDeviceToHost, st));
+        JCB_CUDA(cudaMemcpyAsync(TT, dTT, (size_t)nlv * 8, cudaMemcpyDeviceToHost, st));
+    }
+    JCB_CUDA(cudaMemcpyAsync(xmeans, dxm, p * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(xscales, dxs, p * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(ymeans, dym, q * 8, cudaMemcpyDeviceToHost, st));
+    JCB_CUDA(cudaMemcpyAsync(yscales, dys, q * 8, cudaMemcpyDeviceToHost, st));
+    if (!writeback_xy) JCB_CUDA(cudaMemcpyAsync(&status, d_sumw + 1, 8, cudaMemcpyDeviceToHost, st));
+    JCB_TRY(d2h_2d(c, w_out, n, dwout, ld, n, 1, st));
+    JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));         // the block copies on the copy stream
     phase_end(c, JCB200_T_D2H);
     phase_end(c, JCB200_T_TOTAL);
     JCB_CUDA(cudaStreamSynchronize(st));
