@@ -122,8 +122,9 @@ struct GramParams {
 //  * The A operand (rows of G) is used RAW; only the B operand is centred (and weighted):
 //      acc_ij = sum_k x_ki * w_k (x_kj - c_j)  =  G_ij + c_i s_j ,  s_j = sum_k w_k (x_kj - c_j)
 //    K3 subtracts the rank-one term c_i s_j exactly (s is accumulated by the diagonal units); with the
-//    4K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds that
-//    compete with DMMA for the FP64 pipe.
+//    4K-row pivot s_j is tiny, so nothing is lost to cancellation.  This halves the FP64 adds in front of the
+//    DMMAs (a DADD costs the pipe nothing beside a DMMA stream — bench/fp64_mix.cu — but it is one more link in
+//    the issuing warp's LDS -> DADD -> DMMA chain).
 //  * DIAG units skip the 8x8 blocks below the diagonal and accumulate the column sums; NBC < 4 (edge
 //    and Y blocks) skips empty column blocks; MASKED is the zero-filled tail stage of the unweighted
 //    kernel.  All three are COMPILE-TIME: a predicated-off DMMA/DMUL still occupies the FP64 pipe on
@@ -601,12 +602,12 @@ gram_reduce_kernel(const GroupDesc* __restrict__ groups, const int32_t* __restri
 // ratio[col] = mean^2 / variance of the sample tells how much centring matters for this column.
 //
 // The LAST block to finish takes the data-dependent centring decision (it used to be a kernel of its own):
-// centring costs FP64-pipe cycles that the DMMAs need; when every column has mean^2 <= 64 variance, second
+// centring puts a DADD between every fragment load and its DMMAs; when every column has mean^2 <= 64 variance, second
 // moments about 0 lose at most ~2 digits to the mean (K3 removes it exactly: pivot = 0 is just another pivot),
 // far inside the 1e-10 budget.  pivot[p + q] = 1 (the data need centring), 0 (they do not, and the pivot was
 // zeroed: K1 runs without centring; only with JCB_AUTO_NOCENTER=1, because K1 itself gains nothing from it) or
 // 2 (they do not, but K1 keeps its pivot: the default).  K1 centres whenever the flag is non-zero; the score
-// pass K5, where a DADD beside the DMMAs does cost a DMMA slot, goes centre-free on 0 and 2 (k5_xmul.cu).
+// pass K5, which is 2-3 % faster without the DADDs in front of its DMMAs, goes centre-free on 0 and 2 (k5_xmul.cu).
 __global__ void __launch_bounds__(256)
 pivot_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
              int64_t n, int p, int q, double* __restrict__ pivot, double* __restrict__ ratio,

@@ -128,8 +128,9 @@ xmul_kernel(const XmulParams prm) {
     for (int k = threadIdx.x; k < prm.nchunk * XM_KC; k += XM_THREADS) mu_s[k] = prm.mu[k];
     if (SWEEP)
         for (int k = threadIdx.x; k < prm.ncol * prm.q; k += XM_THREADS) cy_s[k] = prm.Cy[k];
-    // Centring costs two DADDs per k4-step beside six DMMAs, and on sm_100a a DADD issued into a DMMA stream
-    // takes about a DMMA slot of the shared FP64 pipe.  When the fit's pivot pass found every column well
+    // Centring puts two DADDs per k4-step between the fragment load and the six DMMAs that use it (no pipe time —
+    // bench/fp64_mix.cu — but latency in this warp's chain: the centred kernel is 2-3 % slower, 0.885 vs 0.864 ms at
+    // C2).  When the fit's pivot pass found every column well
     // scaled about zero (mean^2 <= 64 var: at most two digits to lose), T = X M - mu'M: raw fragments into
     // the DMMAs and one constant per output column in the epilogue.
     const bool center = SWEEP || !(prm.cflag != nullptr && *prm.cflag != 1.0);
