@@ -404,19 +404,58 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
     phases_reset(c0);
     JCB_CUDA(cudaSetDevice(c0->device));
     phase_begin(c0, JCB200_T_TOTAL);
-    // one pivot for all shards: a strided sample over ALL rows, sent to device 0 ahead of its first chunk
-    JCB_CUDA(cudaEventRecord(c0->chunk_ev[0], c0->stream));
-    JCB_CUDA(cudaStreamWaitEvent(c0->copy_stream, c0->chunk_ev[0], 0));
-    JCB_TRY(host_sample_pivot(c0, X, ldx, Y, ldy, n, p, q, sh[0].d_pivot, c0->copy_stream));
-    JCB_CUDA(cudaEventRecord(c0->mg_ev[1], c0->stream));      // pivot ready for the peers
-    // ---- every device: stream its rows in (its own PCIe link) with K1 on the chunks underneath
+    // ---- every device streams its rows in over its own PCIe link with K1 on row chunks underneath.  Chunks: quarters of
+    // the shard, the last one cut again into 1/8, 1/16, 1/16 — what is left to do when the last byte has landed is K1
+    // on 1/16 of the shard (round 1-2: a whole quarter, or the whole shard below 200 000 rows).
+    std::vector<int64_t> bounds[8];
+    for (int d = 0; d < nd; ++d) {
+        const int64_t nr = sh[d].nr;
+        std::vector<int64_t>& b = bounds[d];
+        b.push_back(0);
+        if (nr >= 60000) {
+            const int64_t chunk = (((nr + 3) / 4) + 1) & ~(int64_t)1;
+            while (nr - b.back() > chunk) b.push_back(b.back() + chunk);
+            const int64_t rest = nr - b.back();
+            const int64_t half = ((rest / 2) + 1) & ~(int64_t)1, quarter = ((rest / 4) + 1) & ~(int64_t)1;
+            if (quarter >= 2048) {
+                b.push_back(b.back() + half);
+                b.push_back(b.back() + quarter);
+            }
+        }
+        if (nr > 0) b.push_back(nr);
+    }
+    auto copy_chunk = [&](int d, int ci) -> int {          // rows of chunk ci of device d; lands = blk_ev[ci]
+        Ctx* c = dev_ctx(d);
+        Shard& s = sh[d];
+        const int64_t c0r = bounds[d][ci], nr = bounds[d][ci + 1] - c0r;
+        JCB_TRY(h2d_2d(c, s.dX + c0r, s.ld, X + s.r0 + c0r, ldx, nr, p, c->copy_stream));
+        JCB_TRY(h2d_2d(c, s.dY + c0r, s.ld, Y + s.r0 + c0r, ldy, nr, q, c->copy_stream));
+        JCB_CUDA(cudaEventRecord(c->blk_ev[ci], c->copy_stream));
+        return 0;
+    };
+    // pass 1: the first chunk of every device goes onto its link at once
     for (int d = 0; d < nd; ++d) {
         Ctx* c = dev_ctx(d);
         Shard& s = sh[d];
         JCB_CUDA(cudaSetDevice(c->device));
-        cudaStream_t st = c->stream, cs = c->copy_stream;
-        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], st));
-        JCB_CUDA(cudaStreamWaitEvent(cs, c->chunk_ev[0], 0));
+        JCB_CUDA(cudaEventRecord(c->chunk_ev[0], c->stream));
+        JCB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
+        if (s.nr > 0) {
+            if (w) JCB_TRY(h2d_2d(c, s.dw, s.ld, w + s.r0, n, s.nr, 1, c->copy_stream));
+            JCB_TRY(copy_chunk(d, 0));
+        }
+    }
+    // pass 2: one pivot for all shards — a strided sample over ALL rows, gathered by the host while the first chunks
+    // are on the links, sent to device 0 right behind its first chunk
+    JCB_CUDA(cudaSetDevice(c0->device));
+    JCB_TRY(host_sample_pivot(c0, X, ldx, Y, ldy, n, p, q, sh[0].d_pivot, c0->copy_stream));
+    JCB_CUDA(cudaEventRecord(c0->mg_ev[1], c0->stream));      // pivot ready for the peers
+    // pass 3: K1 on every chunk as it lands, the next chunk's copy queued right behind the launch
+    for (int d = 0; d < nd; ++d) {
+        Ctx* c = dev_ctx(d);
+        Shard& s = sh[d];
+        JCB_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
         if (d > 0) {
             // the pivot was computed on device 0 (from the strided host sample): peer copy
             JCB_CUDA(cudaStreamWaitEvent(st, c0->mg_ev[1], 0));
@@ -425,16 +464,11 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         if (s.nr <= 0) {
             JCB_CUDA(cudaMemsetAsync(s.d_part, 0, plen * 8, st));
         } else {
-            if (w) JCB_TRY(h2d_2d(c, s.dw, s.ld, w + s.r0, n, s.nr, 1, cs));
-            int64_t chunk = s.nr;
-            if (s.nr >= 200000) chunk = (((s.nr + 3) / 4) + 1) & ~(int64_t)1;
-            const int nch = (int)((s.nr + chunk - 1) / chunk);
+            const int nch = (int)bounds[d].size() - 1;
             for (int ci = 0; ci < nch; ++ci) {
-                const int64_t c0r = (int64_t)ci * chunk, nr = std::min(chunk, s.nr - c0r);
-                JCB_TRY(h2d_2d(c, s.dX + c0r, s.ld, X + s.r0 + c0r, ldx, nr, p, cs));
-                JCB_TRY(h2d_2d(c, s.dY + c0r, s.ld, Y + s.r0 + c0r, ldy, nr, q, cs));
-                JCB_CUDA(cudaEventRecord(c->chunk_ev[1 + (ci & 1)], cs));
-                JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[1 + (ci & 1)], 0));
+                const int64_t c0r = bounds[d][ci], nr = bounds[d][ci + 1] - c0r;
+                if (ci > 0) JCB_TRY(copy_chunk(d, ci));
+                JCB_CUDA(cudaStreamWaitEvent(st, c->blk_ev[ci], 0));
                 JCB_TRY(launch_gram(c, s.dX + c0r, s.ld, s.dY + c0r, s.ld, s.dw ? s.dw + c0r : nullptr, nr, p, q,
                                     s.d_pivot, s.d_part, ci > 0));
             }
@@ -455,13 +489,34 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         JCB_TRY(launch_solve(c, s.d_packed, s.d_pivot, p, q, nlv, scal, s.dP, s.dR, s.dW, s.dC, s.dTT, s.dxm,
                              s.dxs, s.dym, s.dys, s.d_sumw));
         if (s.nr > 0) {
-            if (nlv > 0) JCB_TRY(launch_fit_scores(c, s.dX, s.ld, s.nr, p, q, s.dxm, s.dxs, s.dR, nlv, s.d_pivot, s.dT, s.ld));
+            // scores in row blocks, each block's copy to the host (copy stream) under the next blocks' K5; all kernels
+            // are enqueued before the copies
+            const int nblk = (nlv > 0 && s.nr >= 100000) ? 4 : 1;
+            int64_t blk = (s.nr + nblk - 1) / nblk;
+            blk = (blk + 1) & ~(int64_t)1;
+            int nb_used = 0;
+            if (nlv > 0)
+                for (int64_t b0 = 0; b0 < s.nr; b0 += blk, ++nb_used) {
+                    const int64_t nrb = std::min(blk, s.nr - b0);
+                    JCB_TRY(launch_fit_scores(c, s.dX + b0, s.ld, nrb, p, q, s.dxm, s.dxs, s.dR, nlv, s.d_pivot,
+                                              s.dT + b0, s.ld));
+                    JCB_CUDA(cudaEventRecord(c->blk_ev[nb_used], st));
+                }
             JCB_TRY(launch_weights(c, s.dw, s.nr, s.d_sumw, s.dwout));
             if (writeback) {
                 JCB_TRY(launch_center_scale(c, s.dX, s.ld, s.nr, p, s.dxm, s.dxs));
                 JCB_TRY(launch_center_scale(c, s.dY, s.ld, s.nr, q, s.dym, s.dys));
             }
-            if (nlv > 0) JCB_TRY(d2h_2d(c, T + s.r0, ldt, s.dT, s.ld, s.nr, nlv, st));
+            if (nlv > 0) {
+                int bi = 0;
+                for (int64_t b0 = 0; b0 < s.nr; b0 += blk, ++bi) {
+                    const int64_t nrb = std::min(blk, s.nr - b0);
+                    JCB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->blk_ev[bi], 0));
+                    JCB_TRY(d2h_2d(c, T + s.r0 + b0, ldt, s.dT + b0, s.ld, nrb, nlv, c->copy_stream));
+                }
+                JCB_CUDA(cudaEventRecord(c->chunk_ev[0], c->copy_stream));
+                JCB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));
+            }
             JCB_TRY(d2h_2d(c, w_out + s.r0, n, s.dwout, s.ld, s.nr, 1, st));
             if (writeback) {
                 JCB_TRY(d2h_2d(c, X + s.r0, ldx, s.dX, s.ld, s.nr, p, st));
@@ -595,7 +650,10 @@ static void destroy_ctx(Ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_buf(c->partials);
-    free_buf(c->sched_dev);
+    for (int i = 0; i < Ctx::NSCHED; ++i) {
+        free_buf(c->sched[i].dev);
+        c->sched[i] = Ctx::Sched();
+    }
     free_buf(c->pivot_ws);
     c->pivot_ctr_zeroed = c->pivot_ctr_base = nullptr;
     free_buf(c->coef_ws);
@@ -617,7 +675,6 @@ static void destroy_ctx(Ctx* c) {
     if (c->sched_host) cudaFreeHost(c->sched_host);
     c->sched_host = nullptr;
     c->sched_host_bytes = 0;
-    c->sk_p = c->sk_q = c->sk_nst = -1;
     for (int i = 0; i < JCB200_NPHASE; ++i)
         for (int k = 0; k < Ctx::PHASE_SLOTS; ++k) {
             cudaEventDestroy(c->ev_begin[i][k]);

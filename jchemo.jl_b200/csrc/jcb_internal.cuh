@@ -57,16 +57,23 @@ struct Ctx {
     cudaStream_t stream = nullptr;   // stream in use (own_stream or external)
     // K1 scratch
     Buf partials;        // split-K partial units
-    Buf sched_dev;       // device copy of the schedule
-    void* sched_host = nullptr;  // pinned staging for the schedule
+    void* sched_host = nullptr;  // pinned staging for a new schedule
     size_t sched_host_bytes = 0;
-    // schedule cache key
-    int64_t sk_p = -1, sk_q = -1, sk_nst = -1;
-    int sk_ngroups = 0, sk_nsegs = 0;
-    int64_t sk_zone_len = 0;
+    // K1 schedules, cached by (columns seen by the kernel, stages): a streamed fit launches K1 on row chunks of up to
+    // three different lengths per call, and a cache miss drains the stream
+    struct Sched {
+        int64_t p = -1, q = -1, nst = -1;
+        int ngroups = 0, nsegs = 0;
+        int64_t zone_len = 0;
+        size_t off_segs = 0, off_cta = 0, off_gseg = 0;
+        Buf dev;                 // device copy
+        uint64_t stamp = 0;      // last use
+    };
+    static constexpr int NSCHED = 6;
+    Sched sched[NSCHED];
+    uint64_t sched_clock = 0;
     bool k1_attr_set = false;
     cudaEvent_t mg_ev[2];           // multi-GPU: [0] pivot / packed ready, [1] reduced
-    size_t sk_off_segs = 0, sk_off_cta = 0, sk_off_gseg = 0;
     // solve / xmul scratch
     Buf pivot_ws;
     void* pivot_ctr_zeroed = nullptr;   // where the pivot kernel's completion counter was last zeroed

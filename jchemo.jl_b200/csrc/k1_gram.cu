@@ -1012,8 +1012,15 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     const bool joint = joint_ok && dY == dX + p * ldx && ldy == ldx;
     const int64_t pj = joint ? p + q : p, qj = joint ? 0 : q;      // what the kernel sees
     const int nbx = (int)((pj + CB - 1) / CB);
-    // ---- schedule (cached on (pj, qj, nstages))
-    if (c->sk_p != pj || c->sk_q != qj || c->sk_nst != nstages) {
+    // ---- schedule (cached on (pj, qj, nstages); a few entries: the streamed fits launch K1 on chunks of up to three
+    // lengths per call, and a miss drains the stream)
+    Ctx::Sched* sc = nullptr;
+    for (int i = 0; i < Ctx::NSCHED; ++i)
+        if (c->sched[i].p == pj && c->sched[i].q == qj && c->sched[i].nst == nstages) sc = &c->sched[i];
+    if (!sc) {
+        sc = &c->sched[0];
+        for (int i = 1; i < Ctx::NSCHED; ++i)
+            if (c->sched[i].stamp < sc->stamp) sc = &c->sched[i];          // least recently used
         Schedule S;
         build_groups(pj, qj, S);
         // zone = the row range all CTAs sweep together; sized so that one zone of [X Y] (~25 MB) stays
@@ -1029,43 +1036,45 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
             zone_len = std::max<int64_t>(16, rows / KT);
             if (zone_len > nstages) zone_len = nstages;
         }
-        c->sk_zone_len = zone_len;
         build_segments(nstages, ncta, zone_len, S);
         auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
         const size_t gb = up16(S.groups.size() * sizeof(GroupDesc)),
                      sb = up16(S.segs.size() * sizeof(SegDesc)), cb = up16(S.cta_seg.size() * 4),
                      qb = up16(S.group_seg.size() * 4);
         const size_t tot = gb + sb + cb + qb;
+        // a previous launch may still read the entry that is being replaced, and the staging buffer may still be
+        // on its way to the device: drain the stream before touching either
+        JCB_CUDA(cudaStreamSynchronize(c->stream));
         if (c->sched_host_bytes < tot) {
             if (c->sched_host) cudaFreeHost(c->sched_host);
             JCB_CUDA(cudaMallocHost(&c->sched_host, tot));
             c->sched_host_bytes = tot;
         }
-        JCB_TRY(ensure(c->sched_dev, tot));
-        // a previous launch may still read the old schedule: drain the stream before overwriting
-        JCB_CUDA(cudaStreamSynchronize(c->stream));
+        JCB_TRY(ensure(sc->dev, tot));
         unsigned char* h = (unsigned char*)c->sched_host;
         memset(h, 0, tot);
         memcpy(h, S.groups.data(), S.groups.size() * sizeof(GroupDesc));
         memcpy(h + gb, S.segs.data(), S.segs.size() * sizeof(SegDesc));
         memcpy(h + gb + sb, S.cta_seg.data(), S.cta_seg.size() * 4);
         memcpy(h + gb + sb + cb, S.group_seg.data(), S.group_seg.size() * 4);
-        JCB_CUDA(cudaMemcpyAsync(c->sched_dev.p, h, tot, cudaMemcpyHostToDevice, c->stream));
-        c->sk_off_segs = gb;
-        c->sk_off_cta = gb + sb;
-        c->sk_off_gseg = gb + sb + cb;
-        c->sk_p = pj;
-        c->sk_q = qj;
-        c->sk_nst = nstages;
-        c->sk_ngroups = (int)S.groups.size();
-        c->sk_nsegs = (int)S.segs.size();
+        JCB_CUDA(cudaMemcpyAsync(sc->dev.p, h, tot, cudaMemcpyHostToDevice, c->stream));
+        sc->off_segs = gb;
+        sc->off_cta = gb + sb;
+        sc->off_gseg = gb + sb + cb;
+        sc->p = pj;
+        sc->q = qj;
+        sc->nst = nstages;
+        sc->zone_len = zone_len;
+        sc->ngroups = (int)S.groups.size();
+        sc->nsegs = (int)S.segs.size();
     }
-    const int ng = c->sk_ngroups, nsegs = c->sk_nsegs;
-    unsigned char* d = (unsigned char*)c->sched_dev.p;
+    sc->stamp = ++c->sched_clock;
+    const int ng = sc->ngroups, nsegs = sc->nsegs;
+    unsigned char* d = (unsigned char*)sc->dev.p;
     const GroupDesc* dgroups = (const GroupDesc*)d;
-    const SegDesc* dsegs = (const SegDesc*)(d + c->sk_off_segs);
-    const int32_t* dcta = (const int32_t*)(d + c->sk_off_cta);
-    const int32_t* dgseg = (const int32_t*)(d + c->sk_off_gseg);
+    const SegDesc* dsegs = (const SegDesc*)(d + sc->off_segs);
+    const int32_t* dcta = (const int32_t*)(d + sc->off_cta);
+    const int32_t* dgseg = (const int32_t*)(d + sc->off_gseg);
     JCB_TRY(ensure(c->partials, (size_t)nsegs * NCW * UNIT_STRIDE * 8));
 
     CUtensorMap mapX, mapY, mapW;
@@ -1085,8 +1094,8 @@ int launch_gram_to(Ctx* c, const double* dX, int64_t ldx, const double* dY, int6
     prm.partials = (double*)c->partials.p;
     prm.n = n;
     prm.nst = nstages;
-    prm.zone_len = (int32_t)c->sk_zone_len;
-    prm.nzones = (int32_t)((nstages + c->sk_zone_len - 1) / c->sk_zone_len);
+    prm.zone_len = (int32_t)sc->zone_len;
+    prm.nzones = (int32_t)((nstages + sc->zone_len - 1) / sc->zone_len);
     prm.p = (int)pj;
     prm.q = (int)qj;
     prm.nbx = nbx;
