@@ -491,7 +491,8 @@ static int fit_multi_locked(double* X, int64_t ldx, double* Y, int64_t ldy, cons
         if (s.nr > 0) {
             // scores in row blocks, each block's copy to the host (copy stream) under the next blocks' K5; all kernels
             // are enqueued before the copies
-            const int nblk = (nlv > 0 && s.nr >= 100000) ? 4 : 1;
+            // (blocks below ~100 000 rows cost more in K5's per-launch and tile-quantisation overheads than their copy hides)
+            const int nblk = nlv > 0 ? (s.nr >= 400000 ? 4 : (s.nr >= 200000 ? 2 : 1)) : 1;
             int64_t blk = (s.nr + nblk - 1) / nblk;
             blk = (blk + 1) & ~(int64_t)1;
             int nb_used = 0;
